@@ -1,0 +1,251 @@
+"""Consensus weighted vote on B200 -- the Python call surface of the reference, backed by the
+sm_100a kernels behind ``ds_consensus_vote*`` (include/deep_staple_b200.h).
+
+Reference (multimodallearning/deep_staple):
+* ``calc_dp_consensus(lbl_list, weighting_list)``   deep_staple/consensus/consensus.ipynb:100-109
+* the consensus driver cell                         deep_staple/consensus/consensus.ipynb:353-422
+
+Everything here runs on the GPU; tensors that arrive on the CPU (the notebook works with
+``DEVICE='cpu'``, consensus.ipynb:30) are copied to the current CUDA device, voted on there and the
+result is returned on the device the labels came from.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _binding as _b
+
+__all__ = [
+    "calc_dp_consensus",
+    "consensus_batched",
+    "consensus_sparse",
+    "consensus_multiclass",
+    "consensus_from_snapshot",
+    "group_snapshot",
+]
+
+
+def _cuda_device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("deep_staple_b200 needs a B200 (sm_100a) GPU: no CUDA device is visible and there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"device {device} requested: deep_staple_b200 has no CPU fallback")
+    return device if device.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+def _weights_tensor(weighting_list, device) -> torch.Tensor:
+    """``torch.tensor(weighting_list)`` of consensus.ipynb:103 as an fp32 ``[N]`` device tensor
+    (accepts a tensor, or a list of floats / 0-dim / ``[1]`` tensors like the notebook passes)."""
+    if isinstance(weighting_list, torch.Tensor):
+        w = weighting_list.detach().reshape(-1)
+    else:
+        items = list(weighting_list)
+        if len(items) and isinstance(items[0], torch.Tensor):
+            w = torch.stack([x.detach().reshape(()) for x in items])
+        else:
+            w = torch.tensor([float(x) for x in items], dtype=torch.float32)
+    return w.to(device=device, dtype=torch.float32).contiguous()
+
+
+def consensus_batched(
+    labels: torch.Tensor,
+    data_parameters: torch.Tensor,
+    *,
+    out_dtype: Optional[torch.dtype] = None,
+    count_near_ties: bool = False,
+    weights_are_softmaxed: bool = False,
+    out: Optional[torch.Tensor] = None,
+) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+    """Vote for ``T`` targets in one launch.
+
+    labels            ``[T, N, *spatial]`` int64 or uint8, CUDA, the N registered atlas candidates
+    data_parameters   ``[T, N]`` fp32 raw data parameters (softmax over N taken in-kernel,
+                      consensus.ipynb:103-104) -- or final weights if ``weights_are_softmaxed``
+    returns           ``[T, *spatial]`` (dtype of the labels unless ``out_dtype``), and -- if
+                      ``count_near_ties`` -- a 0-dim int64 tensor with the number of voxels whose
+                      top-two votes differ by < 1e-6 relative (BASELINE.json tolerance clause).
+    """
+    _b.require_cuda(labels, "labels")
+    if labels.dim() < 3:
+        raise ValueError(f"labels must be [T, N, *spatial], got {tuple(labels.shape)}")
+    T, N = labels.shape[0], labels.shape[1]
+    spatial = tuple(labels.shape[2:])
+    lab = labels.contiguous()
+    dps = data_parameters.detach().to(device=lab.device, dtype=torch.float32).reshape(T, N).contiguous()
+    V = lab[0, 0].numel()
+    odt = out_dtype or lab.dtype
+    if out is None:
+        out = torch.empty((T, *spatial), dtype=odt, device=lab.device)
+    elif out.dtype != odt or out.numel() != T * V or not out.is_contiguous() or out.device != lab.device:
+        raise ValueError("out must be a contiguous [T, *spatial] tensor of the output dtype on the labels' device")
+    ties = torch.zeros((), dtype=torch.int64, device=lab.device) if count_near_ties else None
+    lib = _b.load()
+    with torch.cuda.device(lab.device):
+        rc = lib.ds_consensus_vote(
+            _b.ptr(lab), _b.label_dtype(lab), _b.ptr(dps), 0 if weights_are_softmaxed else 1, T, N, V,
+            _b.ptr(out), _b.label_dtype(out), _b.ptr(ties), _b.stream_ptr(lab.device),
+        )
+    _b.check(rc, "ds_consensus_vote")
+    return (out, ties) if count_near_ties else out
+
+
+def _flatten_sparse(lbls: Sequence[torch.Tensor], device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, tuple]:
+    """Sparse-COO label tensors -> (linear voxel index, values, segment offsets) on ``device``.
+    ``coalesce()`` sorts the indices lexicographically, i.e. by linear index."""
+    shape = tuple(lbls[0].shape)
+    strides = []
+    acc = 1
+    for s in reversed(shape):
+        strides.append(acc)
+        acc *= s
+    strides = torch.tensor(list(reversed(strides)), dtype=torch.int64, device=device)
+    idx_parts, val_parts, counts = [], [], []
+    for l in lbls:
+        if tuple(l.shape) != shape:
+            raise ValueError("all label candidates must have the same shape")
+        l = l.coalesce() if not l.is_coalesced() else l
+        ind = l.indices().to(device)
+        idx_parts.append((ind * strides[:, None]).sum(0))
+        val_parts.append(l.values().to(device=device, dtype=torch.int64))
+        counts.append(ind.shape[1])
+    voxel_index = torch.cat(idx_parts) if idx_parts else torch.empty(0, dtype=torch.int64, device=device)
+    values = torch.cat(val_parts)
+    offsets = torch.zeros(len(lbls) + 1, dtype=torch.int64)
+    offsets[1:] = torch.tensor(counts, dtype=torch.int64).cumsum(0)
+    return voxel_index.contiguous(), values.contiguous(), offsets.to(device), shape
+
+
+def consensus_sparse(
+    lbls: Sequence[torch.Tensor],
+    weighting_list,
+    *,
+    device=None,
+    out_dtype: torch.dtype = torch.int64,
+    count_near_ties: bool = False,
+):
+    """Vote straight from sparse-COO candidates (the snapshot's ``modified_labels[i]``) without
+    ``torch.stack`` + ``to_dense`` (consensus.ipynb:102,105): only the stored elements are moved to
+    and read on the GPU.  Same result bits as the dense kernel."""
+    dev = _cuda_device(device if device is not None else (lbls[0].device if lbls[0].is_cuda else None))
+    voxel_index, values, offsets, shape = _flatten_sparse(lbls, dev)
+    w = _weights_tensor(weighting_list, dev)
+    N = len(lbls)
+    if w.numel() != N:
+        raise ValueError(f"{N} label candidates but {w.numel()} weights")
+    V = 1
+    for s in shape:
+        V *= s
+    out = torch.empty(shape, dtype=out_dtype, device=dev)
+    ties = torch.zeros((), dtype=torch.int64, device=dev) if count_near_ties else None
+    lib = _b.load()
+    with torch.cuda.device(dev):
+        rc = lib.ds_consensus_vote_sparse(
+            _b.ptr(voxel_index), _b.ptr(values), _b.ptr(offsets), _b.ptr(w), 1, 1, N, V,
+            _b.ptr(out), _b.label_dtype(out), _b.ptr(ties), _b.stream_ptr(dev),
+        )
+    _b.check(rc, "ds_consensus_vote_sparse")
+    return (out, ties) if count_near_ties else out
+
+
+def calc_dp_consensus(lbl_list: Sequence[torch.Tensor], weighting_list, *, device=None, return_near_ties: bool = False):
+    """Drop-in for the reference's ``calc_dp_consensus`` (consensus.ipynb:100-109): fuse N registered
+    label candidates of one target by the softmax of their data parameters and threshold the vote
+    at 0.5.  ``lbl_list``: N tensors ``[D,H,W]`` (any rank), int64 or uint8, sparse COO (as stored
+    in ``train_label_snapshot.pth``) or dense; ``weighting_list``: N raw data parameters (floats,
+    0-dim or ``[1]`` tensors).  Returns a dense int64 tensor on the device of ``lbl_list[0]``."""
+    lbls = list(lbl_list)
+    if not lbls:
+        raise ValueError("lbl_list is empty")
+    src_device = lbls[0].device
+    if lbls[0].is_sparse:
+        res = consensus_sparse(lbls, weighting_list, device=device, count_near_ties=return_near_ties)
+    else:
+        dev = _cuda_device(device if device is not None else (src_device if src_device.type == "cuda" else None))
+        if any(l.dtype != lbls[0].dtype for l in lbls):
+            lbls = [l.long() for l in lbls]
+        if lbls[0].dtype not in (torch.int64, torch.uint8):
+            lbls = [l.long() for l in lbls]
+        stack = torch.stack([l.to(dev, non_blocking=True) for l in lbls]).unsqueeze(0)  # [1, N, *S]
+        w = _weights_tensor(weighting_list, dev)
+        if w.numel() != len(lbls):
+            raise ValueError(f"{len(lbls)} label candidates but {w.numel()} weights")
+        res = consensus_batched(stack, w.reshape(1, -1), out_dtype=torch.int64, count_near_ties=return_near_ties)
+        res = (res[0][0], res[1]) if return_near_ties else res[0]
+    if return_near_ties:
+        return res[0].to(src_device), int(res[1].item())
+    return res.to(src_device)
+
+
+def consensus_multiclass(labels: torch.Tensor, data_parameters: torch.Tensor, num_classes: int,
+                         *, out_dtype: Optional[torch.dtype] = None, weights_are_softmaxed: bool = False) -> torch.Tensor:
+    """EXTENSION without a reference counterpart: per-class weighted vote + argmax (ties -> lowest
+    class index) over ``labels [T, N, *spatial]``."""
+    _b.require_cuda(labels, "labels")
+    T, N = labels.shape[0], labels.shape[1]
+    lab = labels.contiguous()
+    dps = data_parameters.detach().to(device=lab.device, dtype=torch.float32).reshape(T, N).contiguous()
+    out = torch.empty((T, *lab.shape[2:]), dtype=out_dtype or lab.dtype, device=lab.device)
+    lib = _b.load()
+    with torch.cuda.device(lab.device):
+        rc = lib.ds_consensus_vote_multiclass(
+            _b.ptr(lab), _b.label_dtype(lab), _b.ptr(dps), 0 if weights_are_softmaxed else 1, T, N,
+            lab[0, 0].numel(), int(num_classes), _b.ptr(out), _b.label_dtype(out), _b.stream_ptr(lab.device),
+        )
+    _b.check(rc, "ds_consensus_vote_multiclass")
+    return out
+
+
+def group_snapshot(snapshot: Dict) -> Dict[str, Dict]:
+    """consensus.ipynb:353-377: group the snapshot by fixed (target) id.  Ids look like
+    ``'126l:m102l'``: fixed id ``_id[:4]``, moving (atlas) id ``_id[6:]``; the first entry of a fixed
+    id supplies ``expert_label`` and ``prediction``."""
+    d_ids = snapshot["d_ids"]
+    first_index = {}
+    for k, _id in enumerate(d_ids):
+        first_index.setdefault(_id, k)  # the notebook uses d_ids.index(_id): first occurrence
+    consensus_dicts: Dict[str, Dict] = {}
+    for _id in d_ids:
+        k = first_index[_id]
+        f_id, m_id = _id[:4], _id[6:]
+        fixed = consensus_dicts.get(f_id)
+        if fixed is None:
+            fixed = {"expert_label": snapshot["labels"][k], "prediction": snapshot["train_predictions"][k]}
+        moving = fixed.get(m_id, {})
+        moving["warped_label"] = snapshot["modified_labels"][k]
+        moving["data_parameter"] = snapshot["data_parameters"][k]
+        fixed[m_id] = moving
+        consensus_dicts[f_id] = fixed
+    return consensus_dicts
+
+
+def consensus_from_snapshot(snapshot, *, device=None, with_dice: bool = True) -> Dict[str, Dict]:
+    """The consensus driver cell (consensus.ipynb:353-418) minus the SimpleITK STAPLE baseline:
+    ``snapshot`` is the dict saved as ``train_label_snapshot.pth`` (main_deep_staple.py:963-1037) or
+    a path to it.  Per target: vote over all its registered candidates, Dice against the expert label,
+    results stored under ``dp_consensus`` (sparse, like the notebook) / ``dp_consensus_oracle_dice``."""
+    if isinstance(snapshot, (str, bytes)) or hasattr(snapshot, "__fspath__"):
+        from .snapshot import load_snapshot
+
+        snapshot = load_snapshot(snapshot)
+    dicts = group_snapshot(snapshot)
+    for f_id, fixed in dicts.items():
+        entries = [e for e in fixed.values() if isinstance(e, dict)]
+        lbls: List[torch.Tensor] = [e["warped_label"] for e in entries]
+        dps = [e["data_parameter"] for e in entries]
+        cons = calc_dp_consensus(lbls, dps, device=device)
+        fixed["dp_consensus"] = cons.to_sparse()
+        if with_dice:
+            from .metrics import dice_from_label_maps
+
+            expert = fixed["expert_label"]
+            expert = expert.to_dense() if expert.is_sparse else expert
+            fixed["dp_consensus_oracle_dice"] = dice_from_label_maps(
+                cons.unsqueeze(0), expert.unsqueeze(0), 2, nan_for_unlabeled_target=False
+            )
+        dicts[f_id] = fixed
+    return dicts

@@ -1,0 +1,39 @@
+// Host-side dispatch of loss_kernel over (label dtype, class count, vector width, outputs).
+#pragma once
+
+#include "ds_loss.cuh"
+
+namespace ds {
+
+template <typename LT, typename TT, int C, int VEC>
+int launch_cfg(const LossParams& p, bool grad, bool stats, cudaStream_t stream) {
+  const dim3 grid((unsigned)(p.B_local * p.chunks));
+  if (grad && stats)
+    loss_kernel<LT, TT, C, VEC, true, true><<<grid, kThreads, 0, stream>>>(p);
+  else if (stats)
+    loss_kernel<LT, TT, C, VEC, false, true><<<grid, kThreads, 0, stream>>>(p);
+  else
+    loss_kernel<LT, TT, C, VEC, true, false><<<grid, kThreads, 0, stream>>>(p);
+  count_launch();
+  return check_launch("loss_kernel");
+}
+
+template <typename LT, typename TT>
+int launch_tt(const LossParams& p, bool grad, bool stats, bool vec, cudaStream_t stream) {
+  if (!vec) return launch_cfg<LT, TT, 0, 1>(p, grad, stats, stream);
+  constexpr int W = sizeof(LT) == 4 ? 4 : 8;
+  switch (p.C) {
+    case 2: return launch_cfg<LT, TT, 2, W>(p, grad, stats, stream);
+    case 3: return launch_cfg<LT, TT, 3, W>(p, grad, stats, stream);
+    case 4: return launch_cfg<LT, TT, 4, W>(p, grad, stats, stream);
+    default: return launch_cfg<LT, TT, 0, 4>(p, grad, stats, stream);
+  }
+}
+
+template <typename LT>
+int launch_loss_typed(const LossParams& p, int target_dtype, bool grad, bool stats, bool vec, cudaStream_t stream) {
+  return target_dtype == DS_I64 ? launch_tt<LT, int64_t>(p, grad, stats, vec, stream)
+                                : launch_tt<LT, uint8_t>(p, grad, stats, vec, stream);
+}
+
+}  // namespace ds

@@ -1,0 +1,329 @@
+// Consensus weighted vote (dense label planes).
+//
+// Replaces calc_dp_consensus, deep_staple/consensus/consensus.ipynb:100-109 of the reference:
+//   w = softmax(data parameters of the N candidates of one target)          (:103-104)
+//   S[v] = sum_n float(label_n[v]) * w_n   (int64 * fp32 -> fp32, sum(0))   (:105-106)
+//   consensus[v] = S[v] > 0.5                                               (:107)
+//
+// HBM-bound streaming kernel: every thread owns VPT consecutive voxels, walks the N candidate
+// planes with 128-bit streaming loads (BATCH candidates in flight), keeps the vote in registers
+// and reproduces the summation ORDER of ATen's CPU sum(dim=0) (rows sequential inside blocks of
+// 16, each full block folded into the next accumulator level), so that for identical weights the
+// fp32 vote -- and therefore the thresholded label -- is bit-identical to the reference.
+#include "ds_common.cuh"
+
+namespace ds {
+namespace {
+
+constexpr int kWChunk = 4096;  // candidate weights staged in shared memory per pass
+constexpr int kBatch = 8;      // candidate planes whose loads are in flight together (divides 16)
+
+template <typename LT, bool VECP>
+struct VoteIn;
+template <>
+struct VoteIn<int64_t, true> {
+  static constexpr int VPT = 4;  // 2 x 16 B
+  struct Raw {
+    uint4 a, b;
+  };
+  static __device__ __forceinline__ Raw load(const int64_t* p) { return {ldg_stream16(p), ldg_stream16(p + 2)}; }
+  static __device__ __forceinline__ void to_float(const Raw& r, float (&f)[VPT]) {
+    f[0] = __ll2float_rn((long long)(((unsigned long long)r.a.y << 32) | r.a.x));
+    f[1] = __ll2float_rn((long long)(((unsigned long long)r.a.w << 32) | r.a.z));
+    f[2] = __ll2float_rn((long long)(((unsigned long long)r.b.y << 32) | r.b.x));
+    f[3] = __ll2float_rn((long long)(((unsigned long long)r.b.w << 32) | r.b.z));
+  }
+};
+template <>
+struct VoteIn<int64_t, false> {
+  static constexpr int VPT = 1;
+  struct Raw {
+    long long a;
+  };
+  static __device__ __forceinline__ Raw load(const int64_t* p) { return {__ldg((const long long*)p)}; }
+  static __device__ __forceinline__ void to_float(const Raw& r, float (&f)[VPT]) { f[0] = __ll2float_rn(r.a); }
+};
+template <>
+struct VoteIn<uint8_t, true> {
+  static constexpr int VPT = 16;  // 1 x 16 B
+  struct Raw {
+    uint4 a;
+  };
+  static __device__ __forceinline__ Raw load(const uint8_t* p) { return {ldg_stream16(p)}; }
+  static __device__ __forceinline__ void to_float(const Raw& r, float (&f)[VPT]) {
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[4 * i + j] = (float)((w[i] >> (8 * j)) & 0xffu);
+    }
+  }
+};
+template <>
+struct VoteIn<uint8_t, false> {
+  static constexpr int VPT = 1;
+  struct Raw {
+    uint8_t a;
+  };
+  static __device__ __forceinline__ Raw load(const uint8_t* p) { return {__ldg(p)}; }
+  static __device__ __forceinline__ void to_float(const Raw& r, float (&f)[VPT]) { f[0] = (float)r.a; }
+};
+
+template <typename OT, int VPT>
+__device__ __forceinline__ void store_labels(OT* p, const bool (&on)[VPT]) {
+  if constexpr (sizeof(OT) == 8) {
+    if constexpr (VPT % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < VPT; i += 2) stg_stream16(p + i, make_uint4(on[i] ? 1u : 0u, 0u, on[i + 1] ? 1u : 0u, 0u));
+    } else {
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) p[i] = on[i] ? 1 : 0;
+    }
+  } else {
+    if constexpr (VPT == 16) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        w[i] = (on[4 * i] ? 1u : 0u) | (on[4 * i + 1] ? 0x100u : 0u) | (on[4 * i + 2] ? 0x10000u : 0u) |
+               (on[4 * i + 3] ? 0x1000000u : 0u);
+      stg_stream16(p, make_uint4(w[0], w[1], w[2], w[3]));
+    } else if constexpr (VPT == 4) {
+      stg_stream4(p, (on[0] ? 1u : 0u) | (on[1] ? 0x100u : 0u) | (on[2] ? 0x10000u : 0u) | (on[3] ? 0x1000000u : 0u));
+    } else {
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) p[i] = on[i] ? 1 : 0;
+    }
+  }
+}
+
+struct VoteParams {
+  const void* labels;
+  const float* weights;
+  void* out;
+  unsigned long long* near_ties;
+  int64_t T, N, V;
+  int64_t units;   // V / VPT
+  int chunks;      // CTAs per target
+  int raw;         // weights are raw data parameters -> softmax in kernel
+};
+
+// softmax statistics of the N data parameters of target t: row max and 1/sum(exp(x - max)),
+// the two quantities torch.softmax's CPU kernel forms before scaling (consensus.ipynb:104).
+__device__ __forceinline__ void softmax_stats(const float* __restrict__ dp, int64_t N, float* s_f, float& mx,
+                                              float& inv) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int64_t n = threadIdx.x; n < N; n += kThreads) m = fmaxf(m, __ldg(dp + n));
+  m = warp_max(m);
+  if (lane == 0) s_f[warp] = m;
+  __syncthreads();
+  m = s_f[0];
+#pragma unroll
+  for (int w = 1; w < kWarps; ++w) m = fmaxf(m, s_f[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int64_t n = threadIdx.x; n < N; n += kThreads) s += expf(__ldg(dp + n) - m);
+  s = warp_sum(s);
+  if (lane == 0) s_f[warp] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) s += s_f[w];
+  __syncthreads();
+  mx = m;
+  inv = 1.0f / s;
+}
+
+template <typename LT, typename OT, int LEVELS, bool TIES, bool VECP>
+__global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
+  using In = VoteIn<LT, VECP>;
+  constexpr int VPT = In::VPT;
+  extern __shared__ float s_w[];
+  __shared__ float s_f[kWarps];
+  __shared__ double s_wtot;
+  __shared__ unsigned int s_ties;
+
+  const int64_t t = blockIdx.x / p.chunks;
+  const int chunk = blockIdx.x % p.chunks;
+  const int64_t N = p.N, V = p.V;
+  const float* __restrict__ wrow = p.weights + t * N;
+
+  float mx = 0.f, inv = 1.f;
+  if (p.raw) softmax_stats(wrow, N, s_f, mx, inv);
+  auto fill = [&](int64_t n0, int nn) {
+    for (int i = threadIdx.x; i < nn; i += kThreads) {
+      const float x = __ldg(wrow + n0 + i);
+      s_w[i] = p.raw ? expf(x - mx) * inv : x;
+    }
+  };
+  const bool single = N <= kWChunk;
+  if (threadIdx.x == 0) s_ties = 0u;
+  if (single) fill(0, (int)N);
+  __syncthreads();
+  double wtot = 0.0;
+  if (TIES) {  // total weight W (fp64 sum of the fp32 weights), the reference of the "other" vote W - S
+    if (single) {
+      if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int i = 0; i < (int)N; ++i) a += (double)s_w[i];
+        s_wtot = a;
+      }
+    } else if (threadIdx.x == 0) {
+      double a = 0.0;
+      for (int64_t i = 0; i < N; ++i) {
+        const float x = __ldg(wrow + i);
+        a += (double)(p.raw ? expf(x - mx) * inv : x);
+      }
+      s_wtot = a;
+    }
+    __syncthreads();
+    wtot = s_wtot;
+  }
+
+  const int64_t u0 = p.units * chunk / p.chunks, u1 = p.units * (chunk + 1) / p.chunks;
+  const LT* __restrict__ lab_t = reinterpret_cast<const LT*>(p.labels) + t * N * V;
+  OT* __restrict__ out_t = reinterpret_cast<OT*>(p.out) + t * V;
+  unsigned int my_ties = 0u;
+
+  for (int64_t base = u0; base < u1; base += kThreads) {
+    const int64_t u = base + threadIdx.x;
+    const bool active = u < u1;
+    float acc[LEVELS][VPT];
+#pragma unroll
+    for (int l = 0; l < LEVELS; ++l)
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) acc[l][i] = 0.f;
+
+    for (int64_t n0 = 0; n0 < N; n0 += kWChunk) {
+      const int nn = (int)((N - n0) < kWChunk ? (N - n0) : kWChunk);
+      if (!single) {
+        __syncthreads();
+        fill(n0, nn);
+        __syncthreads();
+      }
+      if (active) {
+        const LT* __restrict__ pl = lab_t + n0 * V + u * VPT;
+        for (int nb = 0; nb < nn; nb += kBatch) {
+          typename In::Raw raw[kBatch];
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j)
+            if (nb + j < nn) raw[j] = In::load(pl + (int64_t)j * V);
+          pl += (int64_t)kBatch * V;
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j) {
+            if (nb + j < nn) {
+              const float w = s_w[nb + j];
+              float f[VPT];
+              In::to_float(raw[j], f);
+              // product and sum rounded separately, like ATen's mul followed by sum (no FMA)
+#pragma unroll
+              for (int i = 0; i < VPT; ++i) acc[0][i] = __fadd_rn(acc[0][i], __fmul_rn(f[i], w));
+            }
+          }
+          // ATen cascade: after every full block of 16 rows fold level 0 into level 1, after
+          // every 256 rows level 1 into level 2, after every 4096 rows level 2 into level 3
+          const int64_t done = n0 + nb + kBatch;  // rows consumed if this batch was full
+          if constexpr (LEVELS > 1) {
+            if ((done & 15) == 0 && done <= N) {
+#pragma unroll
+              for (int i = 0; i < VPT; ++i) acc[1][i] = __fadd_rn(acc[1][i], acc[0][i]), acc[0][i] = 0.f;
+              if constexpr (LEVELS > 2) {
+                if ((done & 255) == 0) {
+#pragma unroll
+                  for (int i = 0; i < VPT; ++i) acc[2][i] = __fadd_rn(acc[2][i], acc[1][i]), acc[1][i] = 0.f;
+                  if ((done & 4095) == 0) {
+#pragma unroll
+                    for (int i = 0; i < VPT; ++i) acc[3][i] = __fadd_rn(acc[3][i], acc[2][i]), acc[2][i] = 0.f;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (active) {
+      bool on[VPT];
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        float s = acc[0][i];
+#pragma unroll
+        for (int l = 1; l < LEVELS; ++l) s = __fadd_rn(s, acc[l][i]);
+        on[i] = s > 0.5f;  // strict: ties go to background (consensus.ipynb:107)
+        if (TIES) {
+          const double fg = (double)s, bg = wtot - fg;
+          const double top = fg > bg ? fg : bg;
+          my_ties += (fabs(fg - bg) < 1e-6 * top) ? 1u : 0u;
+        }
+      }
+      store_labels<OT, VPT>(out_t + u * VPT, on);
+    }
+  }
+  if (TIES) {
+    my_ties = (unsigned int)warp_sum((int)my_ties);
+    if ((threadIdx.x & 31) == 0 && my_ties) atomicAdd(&s_ties, my_ties);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_ties) atomicAdd(p.near_ties, (unsigned long long)s_ties);
+  }
+}
+
+template <typename LT, typename OT, bool VECP>
+int launch_vote(const VoteParams& p0, cudaStream_t stream) {
+  VoteParams p = p0;
+  constexpr int VPT = VoteIn<LT, VECP>::VPT;
+  p.units = p.V / VPT;
+  // grid: T targets x chunks, about `waves` full waves of resident CTAs, at least one iteration each
+  const int sms = sm_count();
+  const int per_sm = env_int("DS_VOTE_CTAS_PER_SM", 4), waves = env_int("DS_VOTE_WAVES", 4);
+  int64_t want = ((int64_t)sms * per_sm * waves + p.T - 1) / p.T;
+  const int64_t max_chunks = (p.units + kThreads - 1) / kThreads;
+  if (want > max_chunks) want = max_chunks;
+  if (want < 1) want = 1;
+  if (p.T * want > 0x7fffffffLL) return fail(DS_ERR_SHAPE, "ds_consensus_vote: T*chunks exceeds the grid limit");
+  p.chunks = (int)want;
+  const dim3 grid((unsigned)(p.T * want));
+  const size_t smem = (size_t)(p.N < kWChunk ? p.N : kWChunk) * sizeof(float);
+  const bool ties = p.near_ties != nullptr;
+  const int levels = p.N < 32 ? (p.N < 16 ? 1 : 2) : (p.N < 256 ? 2 : 4);
+#define DS_VOTE_LAUNCH(L, TI) vote_kernel<LT, OT, L, TI, VECP><<<grid, kThreads, smem, stream>>>(p)
+  if (levels == 1) {
+    if (ties) DS_VOTE_LAUNCH(1, true); else DS_VOTE_LAUNCH(1, false);
+  } else if (levels == 2) {
+    if (ties) DS_VOTE_LAUNCH(2, true); else DS_VOTE_LAUNCH(2, false);
+  } else {
+    if (ties) DS_VOTE_LAUNCH(4, true); else DS_VOTE_LAUNCH(4, false);
+  }
+#undef DS_VOTE_LAUNCH
+  count_launch();
+  return check_launch("ds_consensus_vote");
+}
+
+template <typename LT, typename OT>
+int dispatch_align(const VoteParams& p, cudaStream_t stream) {
+  constexpr int VPT = VoteIn<LT, true>::VPT;
+  const bool vec = (p.V % VPT == 0) && (reinterpret_cast<uintptr_t>(p.labels) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(p.out) % 16 == 0);
+  return vec ? launch_vote<LT, OT, true>(p, stream) : launch_vote<LT, OT, false>(p, stream);
+}
+
+}  // namespace
+}  // namespace ds
+
+extern "C" int ds_consensus_vote(const void* labels, int label_dtype, const float* weights, int weights_are_raw,
+                                 int64_t T, int64_t N, int64_t V, void* out, int out_dtype,
+                                 unsigned long long* near_tie_count, ds_stream_t stream) {
+  using namespace ds;
+  if (!labels || !weights || !out) return fail(DS_ERR_NULL, "ds_consensus_vote: labels, weights and out are required");
+  if (T <= 0 || N <= 0 || V <= 0) return fail(DS_ERR_SHAPE, "ds_consensus_vote: T, N, V must be positive");
+  if (N > DS_MAX_CANDIDATES) return fail(DS_ERR_SHAPE, "ds_consensus_vote: N=%lld exceeds %d", (long long)N, DS_MAX_CANDIDATES);
+  if ((label_dtype != DS_I64 && label_dtype != DS_U8) || (out_dtype != DS_I64 && out_dtype != DS_U8))
+    return fail(DS_ERR_DTYPE, "ds_consensus_vote: labels/out must be DS_I64 or DS_U8");
+  if (int rc = ds_device_check()) return rc;
+  VoteParams p{};
+  p.labels = labels, p.weights = weights, p.out = out, p.near_ties = near_tie_count;
+  p.T = T, p.N = N, p.V = V, p.raw = weights_are_raw ? 1 : 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (label_dtype == DS_I64)
+    return out_dtype == DS_I64 ? dispatch_align<int64_t, int64_t>(p, s) : dispatch_align<int64_t, uint8_t>(p, s);
+  return out_dtype == DS_I64 ? dispatch_align<uint8_t, int64_t>(p, s) : dispatch_align<uint8_t, uint8_t>(p, s);
+}

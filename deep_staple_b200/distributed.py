@@ -1,0 +1,222 @@
+"""Multi-GPU sharding of the hot path: one process per B200, ``torch.distributed`` (NCCL over
+NVLink 5 / NVSwitch) for the only two exchanges the path needs.  The reference is single process /
+single device (main_deep_staple.py:35-36); this is a new capability, designed from SURVEY.md section 8(e).
+
+* Consensus (consensus.ipynb:382-392): targets are independent -> contiguous block of targets per
+  rank, NO collective while voting; optionally one final all-gather of the label maps and one
+  all-reduce of the near-tie counter.
+* DP loss (main_deep_staple.py:738-762): voxel sums are per instance, but ``weight.mean()`` (:744)
+  and the ``L/B`` term of the gradient couple the whole batch.  Per step:
+    1. all-gather the instances' dataset indices (B_global x 8 bytes) -> every rank draws the data
+       parameters of the WHOLE batch from its embedding replica, so the instance weights are known
+       before the streaming pass and forward + backward still fuse into one sweep;
+    2. the fused kernel writes this rank's rows of the [B_global, C, 4] statistics;
+    3. all-gather of those rows (B_global x C x 32 bytes);
+    4. every rank runs the identical O(B) epilogue -> identical loss and identical sparse gradient
+       rows for all B_global data parameters on every rank: the embedding / SparseAdam replicas stay
+       bit-identical without any gradient all-reduce.
+  The exchange helpers take an explicit process group and work on any backend, so the host logic is
+  covered by world_size-2 gloo tests on CPU (tests/test_distributed_cpu.py) with the kernel call
+  replaced by a stub; on the GPU the kernel calls are the C-ABI ones.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _binding as _b
+
+__all__ = [
+    "shard_range",
+    "gather_batch_indices",
+    "exchange_instance_stats",
+    "sharded_consensus",
+    "dp_weighted_loss_distributed",
+    "global_class_counts",
+]
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block of ``n_items`` owned by ``rank``: sizes differ by at most one, the first
+    ``n_items % world_size`` ranks get the larger blocks (100 targets over 8 GPUs -> 13,13,13,13,12,...)."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def _world(group) -> Tuple[int, int]:
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def gather_batch_indices(idx_local: torch.Tensor, group=None) -> Tuple[torch.Tensor, int]:
+    """All-gather ``b_idxs_dataset`` of every rank -> (``[B_global]`` indices in rank order, row offset
+    of this rank).  Every rank must hold the same number of instances."""
+    rank, world = _world(group)
+    idx_local = idx_local.reshape(-1).contiguous()
+    out = torch.empty(world * idx_local.numel(), dtype=idx_local.dtype, device=idx_local.device)
+    dist.all_gather_into_tensor(out, idx_local, group=group)
+    return out, rank * idx_local.numel()
+
+
+def exchange_instance_stats(stats_full: torch.Tensor, b_offset: int, b_local: int, group=None) -> torch.Tensor:
+    """In-place all-gather of the per-instance statistics: ``stats_full`` is ``[B_global, C, 4]`` with
+    this rank's rows ``[b_offset, b_offset + b_local)`` filled; afterwards all rows are filled on
+    every rank."""
+    mine = stats_full[b_offset : b_offset + b_local]
+    dist.all_gather_into_tensor(stats_full, mine.contiguous(), group=group)
+    return stats_full
+
+
+def global_class_counts(local_counts: torch.Tensor, group=None) -> torch.Tensor:
+    """Label histogram of the GLOBAL batch (normaliser of the class-weighted CE, :716) from the local one."""
+    counts = local_counts.clone()
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def sharded_consensus(
+    labels_local: torch.Tensor,
+    data_parameters_local: torch.Tensor,
+    n_targets_global: int,
+    *,
+    gather: bool = True,
+    count_near_ties: bool = False,
+    group=None,
+    vote_fn: Optional[Callable] = None,
+):
+    """Vote on this rank's block of targets (``labels_local [T_r, N, *S]`` = targets
+    ``shard_range(n_targets_global, rank, world)``); with ``gather`` every rank receives the full
+    ``[T_global, *S]`` stack (one all-gather, the only collective).  Returns ``(maps, near_ties)``."""
+    if vote_fn is None:
+        from .consensus import consensus_batched
+
+        vote_fn = consensus_batched
+    rank, world = _world(group)
+    lo, hi = shard_range(n_targets_global, rank, world)
+    if labels_local.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} owns targets [{lo},{hi}) but got {labels_local.shape[0]} label stacks")
+    ties = None
+    if hi > lo:
+        res = vote_fn(labels_local, data_parameters_local, count_near_ties=count_near_ties)
+        local, ties = res if count_near_ties else (res, None)
+    else:
+        local = torch.empty((0, *labels_local.shape[2:]), dtype=labels_local.dtype, device=labels_local.device)
+    if count_near_ties:
+        ties = ties if ties is not None else torch.zeros((), dtype=torch.int64, device=labels_local.device)
+        ties = ties.clone()
+        dist.all_reduce(ties, op=dist.ReduceOp.SUM, group=group)
+    if not gather:
+        return local, ties
+    # ragged blocks (n_targets % world != 0): pad every block to the largest, gather, cut
+    per = -(-n_targets_global // world)
+    padded = torch.zeros((per, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    full = torch.empty((world * per, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, padded, group=group)
+    parts = []
+    for r in range(world):
+        a, b = shard_range(n_targets_global, r, world)
+        parts.append(full[r * per : r * per + (b - a)])
+    return torch.cat(parts), ties
+
+
+class _DistributedDPLoss(torch.autograd.Function):
+    """Fused local pass + statistics exchange + replicated epilogue (see module docstring)."""
+
+    @staticmethod
+    def forward(ctx, dp_logits, bare_global, target, fixed_global, use_risk, scale, class_w, b_offset, group):
+        from .loss import _flat_inputs, _workspace
+
+        z, t, B_local, C, V = _flat_inputs(dp_logits, target)
+        dev = z.device
+        bare = bare_global.detach().to(torch.float32).reshape(-1).contiguous()
+        B_total = bare.numel()
+        fixed = None if fixed_global is None else fixed_global.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        cw = None if class_w is None else class_w.detach().to(device=dev, dtype=torch.float32).contiguous()
+        need_dlogits = ctx.needs_input_grad[0]
+        dlogits = torch.empty_like(z) if need_dlogits else None
+        stats = torch.zeros((B_total, C, _b.DS_STATS), dtype=torch.float64, device=dev)
+        loss_out = torch.empty(2, dtype=torch.float32, device=dev)
+        d_bare = torch.empty(B_total, dtype=torch.float32, device=dev)
+        per_inst = torch.empty((B_total, _b.DS_INST), dtype=torch.float32, device=dev)
+        lib = _b.load()
+        with torch.cuda.device(dev):
+            ws = _workspace(dev, B_local, C)
+            rc = lib.ds_dp_loss_fwd_bwd(
+                _b.ptr(z), _b.logit_dtype(z), _b.ptr(t), _b.label_dtype(t), None, B_local, C, V, _b.ptr(bare),
+                _b.ptr(fixed), B_total, b_offset, _b.ptr(cw), 1 if use_risk else 0, _b.ptr(scale), _b.ptr(dlogits),
+                _b.ptr(stats), _b.ptr(loss_out), _b.ptr(d_bare), _b.ptr(per_inst), _b.ptr(ws), ws.numel() * 8,
+                _b.stream_ptr(dev),
+            )
+            _b.check(rc, "ds_dp_loss_fwd_bwd")
+            if B_local != B_total:
+                exchange_instance_stats(stats, b_offset, B_local, group)
+                rc = lib.ds_dp_loss_finalize(
+                    _b.ptr(stats), B_total, C, V, _b.ptr(bare), _b.ptr(fixed), _b.ptr(cw), 1 if use_risk else 0,
+                    _b.ptr(scale), _b.ptr(loss_out), _b.ptr(d_bare), _b.ptr(per_inst), _b.stream_ptr(dev),
+                )
+                _b.check(rc, "ds_dp_loss_finalize")
+        ctx.assumed = scale
+        ctx.bare_shape = bare_global.shape
+        ctx.logits_shape = dp_logits.shape
+        ctx.save_for_backward(d_bare, dlogits)
+        ce = loss_out[1]
+        ctx.mark_non_differentiable(ce, per_inst, stats)
+        return loss_out[0], ce, per_inst, stats
+
+    @staticmethod
+    def backward(ctx, grad_loss, _a, _b2, _c):
+        d_bare, dlogits = ctx.saved_tensors
+        g = grad_loss.detach().to(torch.float32).reshape(())
+        ratio = g if ctx.assumed is None else g / ctx.assumed
+        grad_bare = (d_bare * ratio).reshape(ctx.bare_shape)
+        grad_logits = None
+        if dlogits is not None:
+            one = ctx.assumed if ctx.assumed is not None else torch.ones((), dtype=torch.float32, device=g.device)
+            lib = _b.load()
+            with torch.cuda.device(dlogits.device):
+                rc = lib.ds_rescale_inplace(_b.ptr(dlogits), _b.logit_dtype(dlogits), dlogits.numel(), _b.ptr(g),
+                                            _b.ptr(one), _b.stream_ptr(dlogits.device))
+            _b.check(rc, "ds_rescale_inplace")
+            grad_logits = dlogits.view(ctx.logits_shape)
+        return grad_logits, grad_bare, None, None, None, None, None, None, None
+
+
+def dp_weighted_loss_distributed(
+    dp_logits: torch.Tensor,
+    b_seg_modified: torch.Tensor,
+    embedding: torch.nn.Embedding,
+    b_idxs_dataset: torch.Tensor,
+    fixed_weighting: Optional[torch.Tensor] = None,
+    use_risk_regularization: bool = True,
+    *,
+    grad_scaler=None,
+    class_weights: Optional[torch.Tensor] = None,
+    group=None,
+    return_all: bool = False,
+):
+    """Data-parallel form of ``dp_weighted_loss``: each rank passes ITS instances (``dp_logits``,
+    ``b_seg_modified``, ``b_idxs_dataset``), the replicated ``embedding`` and the FULL
+    ``fixed_weighting`` table (:653).  Returns the loss of the GLOBAL batch (identical on every rank);
+    ``backward`` delivers sparse gradient rows for all ``B_global`` data parameters on every rank (so
+    the replicas stay identical) and, if ``dp_logits`` requires grad, this rank's logits gradient."""
+    from .loss import DPLossOutput, _scale_tensor
+
+    idx_global, b_offset = gather_batch_indices(b_idxs_dataset.to(dp_logits.device), group)
+    bare_global = embedding(idx_global).squeeze()  # :741 on the global batch
+    fixed_global = fixed_weighting[idx_global] if fixed_weighting is not None else None  # :748
+    scale = _scale_tensor(grad_scaler, dp_logits.device)
+    loss, ce, per_inst, stats = _DistributedDPLoss.apply(
+        dp_logits, bare_global, b_seg_modified, fixed_global, bool(use_risk_regularization), scale, class_weights,
+        b_offset, group,
+    )
+    if not return_all:
+        return loss
+    return DPLossOutput(
+        dp_loss=loss, ce_loss=ce, per_instance_ce=per_inst[:, _b.DS_INST_CE], fg_pred=per_inst[:, _b.DS_INST_FG],
+        instance_weight=per_inst[:, _b.DS_INST_WEIGHT], inst_stats=stats,
+    )

@@ -1,0 +1,249 @@
+"""GPU parity: fused data-parameter loss / class-weighted CE (CUDA, through the C ABI) vs the
+reference outputs in tests/golden/ and vs the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): loss within 1e-5 relative in fp32, gradients within 1e-4
+relative (relative to the largest gradient magnitude of the tensor; fp16 gradients additionally carry
+their own fp16 rounding, 2^-11 relative per element).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from conftest import golden_names, load_golden
+from oracle import dp_loss as ol
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def _close(a, b, rtol, what, atol=0.0):
+    a = torch.as_tensor(a).double().cpu().reshape(-1)
+    b = torch.as_tensor(b).double().cpu().reshape(-1)
+    scale = float(b.abs().max()) if b.numel() else 0.0
+    err = float((a - b).abs().max()) if b.numel() else 0.0
+    assert err <= rtol * scale + atol, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rtol {rtol})"
+    return err / (scale + 1e-300)
+
+
+def _run_case(g, dev, label_dtype=torch.int64):
+    import deep_staple_b200 as ds
+
+    logits = torch.from_numpy(g["logits"]).to(dev)
+    target = torch.from_numpy(g["target"].astype(np.int64)).to(label_dtype).to(dev)
+    m = g["emb"].shape[0]
+    emb = nn.Embedding(m, 1, sparse=True, _weight=torch.from_numpy(g["emb"]).clone().reshape(m, 1)).to(dev)
+    idx = torch.from_numpy(g["idx"]).to(dev)
+    fixed = torch.from_numpy(g["fixed"]).to(dev)[idx] if bool(g["use_fixed"]) else None
+    cw = torch.from_numpy(g["cw"]).to(dev)
+    scale = float(g["g"])
+    z = logits.clone().requires_grad_(bool(g["need_dlogits"]))
+    bare = emb(idx).squeeze()  # main_deep_staple.py:741
+    out = ds.dp_weighted_loss(z, target, bare, fixed, bool(g["risk"]), grad_scaler=scale, class_weights=cw,
+                              return_all=True)
+    (out.dp_loss * scale).backward()  # scaler_dp.scale(dp_loss).backward(), :762
+    return out, z, emb, idx, cw, logits, target, scale
+
+
+@pytest.mark.parametrize("name", golden_names("loss"))
+@pytest.mark.parametrize("label_dtype", [torch.int64, torch.uint8])
+def test_golden_dp_loss(cuda_device, name, label_dtype):
+    g = load_golden(name)
+    out, z, emb, idx, cw, logits, target, scale = _run_case(g, cuda_device, label_dtype)
+    half = g["logits"].dtype != np.float32
+    _close(out.dp_loss, g["dp_loss"], LOSS_RTOL, "dp_loss")
+    _close(out.ce_loss, g["ce_loss"], LOSS_RTOL, "ce_loss")
+    grad = emb.weight.grad
+    assert grad.is_sparse, "the data-parameter gradient must stay sparse COO (SparseAdam rejects dense grads)"
+    rows = grad.coalesce().to_dense().reshape(-1)[idx]
+    _close(rows, g["d_bare_weight"], GRAD_RTOL, "d_bare_weight", atol=1e-9 * scale)
+    if bool(g["need_dlogits"]):
+        assert z.grad.dtype == z.dtype and z.grad.shape == z.shape
+        _close(z.grad, g["d_logits"], 2e-3 if half else GRAD_RTOL, "d_logits")
+    else:
+        assert z.grad is None
+
+
+@pytest.mark.parametrize("name", golden_names("loss"))
+def test_golden_weighted_ce(cuda_device, name):
+    import deep_staple_b200 as ds
+
+    g = load_golden(name)
+    half = g["logits"].dtype != np.float32
+    z = torch.from_numpy(g["logits"]).to(cuda_device).requires_grad_(True)
+    target = torch.from_numpy(g["target"].astype(np.int64)).to(cuda_device)
+    cw = torch.from_numpy(g["cw"]).to(cuda_device)
+    scale = float(g["g"])
+    ce = ds.weighted_ce(z, target, cw, grad_scaler=scale)
+    (ce * scale).backward()  # scaler.scale(ce_loss).backward(), :719
+    _close(ce, g["ce_loss"], LOSS_RTOL, "ce_loss")
+    _close(z.grad, g["d_logits_ce"], 2e-3 if half else GRAD_RTOL, "d_logits_ce")
+
+
+def test_backward_without_scale_hint_is_reconciled(cuda_device):
+    """No grad_scaler hint: the fused pass assumes g = 1 and backward rescales the stored gradients."""
+    import deep_staple_b200 as ds
+
+    g = load_golden("loss__b4_fp16_scale65536")
+    dev = cuda_device
+    z = torch.from_numpy(g["logits"]).to(dev).requires_grad_(True)
+    target = torch.from_numpy(g["target"].astype(np.int64)).to(dev)
+    bare = torch.from_numpy(g["emb"]).reshape(-1)[torch.from_numpy(g["idx"])].to(dev).requires_grad_(True)
+    fixed = torch.from_numpy(g["fixed"])[torch.from_numpy(g["idx"])].to(dev)
+    loss = ds.dp_weighted_loss(z, target, bare, fixed, True)
+    (loss * float(g["g"])).backward()
+    _close(bare.grad, g["d_bare_weight"], GRAD_RTOL, "d_bare_weight")
+    _close(z.grad, g["d_logits"], 4e-3, "d_logits")  # two fp16 roundings on this path
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("C,shape", [(2, (5, 7, 9)), (3, (4, 4, 8)), (5, (3, 5, 7)), (8, (4, 8, 8)), (2, (33, 17)),
+                                     (4, (16, 24))])
+def test_random_vs_oracle(cuda_device, dtype, C, shape):
+    """odd sizes (scalar path), C up to 8 (run-time class count), half logits, 2D slice mode."""
+    import deep_staple_b200 as ds
+
+    gen = torch.Generator().manual_seed(1000 + C + len(shape))
+    B, M = 3, 10
+    logits = (2 * torch.randn((B, C, *shape), generator=gen)).to(dtype)
+    target = torch.randint(0, C, (B, *shape), generator=gen)
+    emb_w = torch.randn((M, 1), generator=gen)
+    idx = torch.randperm(M, generator=gen)[:B]
+    fixed = torch.rand(M, generator=gen) * 5 + 1
+    cw = torch.rand(C, generator=gen) + 0.5
+    ref = ol.run_loss(logits, target, emb_w, idx, fixed, cw, True, 8.0, True)
+    dev = cuda_device
+    z = logits.to(dev).requires_grad_(True)
+    bare = emb_w.reshape(-1)[idx].to(dev).requires_grad_(True)
+    out = ds.dp_weighted_loss(z, target.to(dev), bare, fixed[idx].to(dev), True, grad_scaler=8.0,
+                              class_weights=cw.to(dev), return_all=True)
+    (out.dp_loss * 8.0).backward()
+    half = dtype != torch.float32
+    _close(out.dp_loss, ref.dp_loss, LOSS_RTOL, "dp_loss")
+    _close(out.ce_loss, ref.ce_loss, LOSS_RTOL, "ce_loss")
+    _close(out.per_instance_ce, ref.per_inst_ce, LOSS_RTOL, "per_instance_ce")
+    assert torch.equal(out.fg_pred.cpu().long(), ref.fg_pred)
+    _close(bare.grad, ref.d_bare_weight, GRAD_RTOL, "d_bare_weight")
+    _close(z.grad.float(), ref.d_logits.float(), (1e-2 if dtype == torch.bfloat16 else 2e-3) if half else GRAD_RTOL, "d_logits")
+    # hard-Dice statistics of the same pass
+    pred = logits.float().argmax(1)
+    for c in range(C):
+        assert int(out.inst_stats[:, c, 1].sum()) == int((target == c).sum())
+        assert int(out.inst_stats[:, c, 2].sum()) == int((pred == c).sum())
+        assert int(out.inst_stats[:, c, 3].sum()) == int(((pred == c) & (target == c)).sum())
+
+
+def test_cfg2_full_size_vs_oracle(cuda_device):
+    """BASELINE.json configs[1]: batch 8 x 2 classes x 128^3, risk regularisation, fwd+bwd."""
+    import deep_staple_b200 as ds
+
+    gen = torch.Generator().manual_seed(0)
+    B, C, S, M = 8, 2, (128, 128, 128), 600
+    logits = 2 * torch.randn((B, C, *S), generator=gen)
+    target = (torch.rand((B, *S), generator=gen) < 0.05).long()
+    emb_w = torch.randn((M, 1), generator=gen)
+    idx = torch.randperm(M, generator=gen)[:B]
+    gt_num = torch.randint(0, 50000, (M,), generator=gen).float()
+    fixed = (gt_num + math.e).log() + math.e
+    counts = torch.bincount(target.reshape(-1), minlength=C).float()
+    cw = 1 / counts.pow(0.35)
+    cw = cw / cw.mean()
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = ol.run_loss(logits, target, emb_w, idx, fixed, cw, True, 65536.0, True)
+    dev = cuda_device
+    z = logits.to(dev).requires_grad_(True)
+    bare = emb_w.reshape(-1)[idx].to(dev).requires_grad_(True)
+    out = ds.dp_weighted_loss(z, target.to(dev), bare, fixed[idx].to(dev), True, grad_scaler=65536.0,
+                              class_weights=cw.to(dev), return_all=True)
+    (out.dp_loss * 65536.0).backward()
+    e1 = _close(out.dp_loss, ref.dp_loss, LOSS_RTOL, "dp_loss")
+    e2 = _close(out.ce_loss, ref.ce_loss, LOSS_RTOL, "ce_loss")
+    e3 = _close(bare.grad, ref.d_bare_weight, GRAD_RTOL, "d_bare_weight")
+    e4 = _close(z.grad, ref.d_logits, GRAD_RTOL, "d_logits")
+    assert torch.equal(out.fg_pred.cpu().long(), ref.fg_pred)
+    print(f"[cfg2] rel err: dp_loss {e1:.2e} ce_loss {e2:.2e} d_bare {e3:.2e} d_logits {e4:.2e}")
+    # run-to-run determinism (fixed-order reductions, no float atomics)
+    z2 = logits.to(dev).requires_grad_(True)
+    out2 = ds.dp_weighted_loss(z2, target.to(dev), bare.detach(), fixed[idx].to(dev), True, grad_scaler=65536.0,
+                               class_weights=cw.to(dev), return_all=True)
+    assert torch.equal(out2.dp_loss, out.dp_loss) and torch.equal(out2.inst_stats, out.inst_stats)
+
+
+def test_two_pass_backward_matches_fused(cuda_device):
+    import deep_staple_b200 as ds
+
+    gen = torch.Generator().manual_seed(9)
+    logits = torch.randn((4, 3, 8, 8, 8), generator=gen).to(cuda_device)
+    target = torch.randint(0, 3, (4, 8, 8, 8), generator=gen).to(cuda_device)
+    bare = torch.randn(4, generator=gen).to(cuda_device)
+    z = logits.clone().requires_grad_(True)
+    out = ds.dp_weighted_loss(z, target, bare, None, True, grad_scaler=4.0, return_all=True)
+    (out.dp_loss * 4.0).backward()
+    two = ds.backward_logits(logits, target, out.instance_weight, 4.0)
+    assert torch.allclose(two, z.grad, rtol=1e-6, atol=1e-12)
+
+
+def test_prepass_and_dice_golden(cuda_device):
+    import deep_staple_b200 as ds
+
+    for name in golden_names("prepass"):
+        g = load_golden(name)
+        labels = torch.from_numpy(g["labels"].astype(np.int64)).to(cuda_device)
+        cw, fw, counts, gt = ds.prepass_constants(labels, int(g["num_classes"]))
+        assert np.array_equal(counts.cpu().numpy(), g["counts"])
+        assert np.array_equal(gt.cpu().numpy(), g["gt_num"])
+        assert np.allclose(cw.cpu().numpy(), g["class_weights"], rtol=1e-6)
+        assert np.allclose(fw.cpu().numpy(), g["fixed_weighting"], rtol=1e-6)
+    for name in golden_names("dice"):
+        g = load_golden(name)
+        for dt in (torch.int64, torch.uint8):
+            d = ds.dice_from_label_maps(torch.from_numpy(g["pred"]).to(dt), torch.from_numpy(g["target"]).to(dt),
+                                        int(g["num_classes"]), bool(g["nan_for_unlabeled_target"]))
+            assert d.device.type == "cpu" and d.dtype == torch.float32
+            assert np.allclose(d.numpy(), g["dice"], rtol=1e-6, atol=0, equal_nan=True)
+
+
+def test_sparse_adam_and_grad_scaler_flow(cuda_device):
+    """The reference's optimiser objects keep working around the op: nn.Embedding(sparse=True) +
+    SparseAdam + GradScaler (main_deep_staple.py:418, 442-445, 762-773)."""
+    import deep_staple_b200 as ds
+
+    torch.manual_seed(0)
+    dev = cuda_device
+    M, B = 50, 4
+    emb = nn.Embedding(M, 1, sparse=True).to(dev)
+    torch.nn.init.normal_(emb.weight.data, mean=0.0, std=0.0)
+    opt = torch.optim.SparseAdam(emb.parameters(), lr=0.1, betas=(0.9, 0.999), eps=1e-8)
+    scaler = torch.amp.GradScaler("cuda")
+    logits = torch.randn((B, 2, 8, 8, 8), device=dev, dtype=torch.float16)
+    target = (torch.rand((B, 8, 8, 8), device=dev) < 0.3).long()
+    idx = torch.tensor([3, 7, 11, 19], device=dev)
+    before = emb.weight.detach().clone()
+    loss = ds.dp_weighted_loss(logits, target, (emb, idx), None, True, grad_scaler=scaler)
+    scaler.scale(loss).backward()
+    scaler.step(opt)
+    scaler.update()
+    assert isinstance(loss.item(), float)
+    changed = (emb.weight.detach() != before).reshape(-1).nonzero().reshape(-1)
+    assert set(changed.tolist()) <= set(idx.tolist()) and len(changed) > 0
+
+
+def test_invalid_arguments_raise(cuda_device):
+    import deep_staple_b200 as ds
+
+    z = torch.zeros((2, 2, 4, 4), device=cuda_device)
+    t = torch.zeros((2, 4, 4), dtype=torch.long, device=cuda_device)
+    with pytest.raises(ValueError):
+        ds.dp_weighted_loss(z, t[:1], torch.zeros(2, device=cuda_device))
+    with pytest.raises(ValueError):
+        ds.dp_weighted_loss(z, t.float(), torch.zeros(2, device=cuda_device))
+    with pytest.raises(ValueError):
+        ds.dp_weighted_loss(z, t, torch.zeros(3, device=cuda_device))
+    with pytest.raises(ValueError):
+        ds.dp_weighted_loss(torch.zeros((2, 9, 4, 4), device=cuda_device), t, torch.zeros(2, device=cuda_device))
+    with pytest.raises(RuntimeError):
+        ds.dp_weighted_loss(z.cpu(), t.cpu(), torch.zeros(2))
