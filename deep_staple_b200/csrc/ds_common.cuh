@@ -168,7 +168,9 @@ struct Logit<__nv_bfloat16> {
 };
 
 // ---------------------------------------------------------------------------------------------
-// labels: load VEC consecutive labels as int (values outside int range saturate to -1 = "no class")
+// labels: load VEC consecutive labels as int.  int64: low word OR high word -- any negative value
+// (torch's ignore_index = -100) becomes negative = "no class"; values >= 2^32 are undefined
+// behaviour in the reference too (device-side assert in torch)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 struct Label;
@@ -176,10 +178,7 @@ struct Label;
 template <>
 struct Label<int64_t> {
   static constexpr int kDtype = DS_I64;
-  static __device__ __forceinline__ int narrow(uint32_t lo, uint32_t hi) {
-    // int64 -> int: anything that does not fit in [0, 2^31) becomes -1
-    return (hi == 0u && (int)lo >= 0) ? (int)lo : -1;
-  }
+  static __device__ __forceinline__ int narrow(uint32_t lo, uint32_t hi) { return (int)(lo | hi); }
   template <int VEC>
   static __device__ __forceinline__ void load(const int64_t* p, int (&t)[VEC]) {
     if constexpr (VEC % 2 == 0) {

@@ -56,6 +56,47 @@ struct LossParams {
 
 __device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
 
+// ---------------------------------------------------------------------------------------------
+// branch-free fp32 math of the per-voxel softmax / log-sum-exp.  The streaming loop is bounded by
+// instruction issue as soon as it spends > ~60 instructions per voxel, so: hardware ex2 / rcp
+// (MUFU, <= 2 ulp) for the exponentials and the softmax denominator, and a range-reduced
+// polynomial log1p whose argument never leaves [0, C-1] (no special cases, no slow path).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// log(1 + r), r >= 0 finite (r = sum of the non-maximal exponentials, <= C - 1).  1 + r = 2^k m with
+// m in [sqrt(1/2), sqrt(2)); for k == 0 the polynomial argument is r itself (exact), so the result
+// keeps full RELATIVE accuracy for confident voxels (r -> 0), unlike log(1 + r) evaluated on the sum.
+// Polynomial: Cephes logf (public domain), |rel err| < 1e-7 on the reduced interval.
+__device__ __forceinline__ float log1p_pos(float r) {
+  const float s = 1.0f + r;
+  const int bits = __float_as_int(s);
+  const int k = (bits - 0x3f3504f3) >> 23;
+  const float m = __int_as_float(bits - (k << 23));
+  const float f = (k == 0) ? r : (m - 1.0f);
+  const float z = f * f;
+  float y = 7.0376836292e-2f;
+  y = fmaf(y, f, -1.1514610310e-1f);
+  y = fmaf(y, f, 1.1676998740e-1f);
+  y = fmaf(y, f, -1.2420140846e-1f);
+  y = fmaf(y, f, 1.4249322787e-1f);
+  y = fmaf(y, f, -1.6668057665e-1f);
+  y = fmaf(y, f, 2.0000714765e-1f);
+  y = fmaf(y, f, -2.4999993993e-1f);
+  y = fmaf(y, f, 3.3333331174e-1f);
+  y = y * f * z;
+  y = fmaf(-0.5f, z, y);
+  return fmaf((float)k, 0.69314718056f, f + y);
+}
+
 // Batch epilogue on reduced statistics.  Called by all kThreads threads of
 // one CTA.  stats are read through L2 (they were just written by other SMs).
 __device__ __forceinline__ void finalize_block(const LossParams& p, double* scratch) {
@@ -181,7 +222,7 @@ __device__ __forceinline__ void publish_stats(const LossParams& p, int b, int ch
 }
 
 // C == 0: class count is a run-time value <= DS_MAX_CLASSES
-template <typename LT, typename TT, int C, int VEC, bool GRAD, bool STATS>
+template <typename LT, typename TT, int C, int VEC, bool GRAD, bool STATS, bool DICE>
 __global__ void __launch_bounds__(kThreads) loss_kernel(const LossParams p) {
   constexpr int CC = C == 0 ? DS_MAX_CLASSES : C;
   const int nc = C == 0 ? p.C : C;
@@ -194,6 +235,8 @@ __global__ void __launch_bounds__(kThreads) loss_kernel(const LossParams p) {
 
   // gradient coefficient per class of the target voxel
   float coef[CC];
+  float coef0 = 0.f;
+  const bool uniform_coef = p.mode != kModeCE;
 #pragma unroll
   for (int c = 0; c < CC; ++c) coef[c] = 0.f;
   if (GRAD) {
@@ -205,13 +248,9 @@ __global__ void __launch_bounds__(kThreads) loss_kernel(const LossParams p) {
       const int64_t bg = p.b_offset + b;
       const double f = p.fixed_w ? (double)__ldg(p.fixed_w + bg) : 1.0;
       const double w = sigmoid_d((double)__ldg(p.bare_weight + bg)) / (m * f);
-      const float cf = (float)(g * w / (double)V);
-#pragma unroll
-      for (int c = 0; c < CC; ++c) coef[c] = cf;
+      coef0 = (float)(g * w / (double)V);
     } else if (p.mode == kModeBwd) {
-      const float cf = (float)(g * (double)__ldg(p.bare_weight + b * p.weight_stride) / (double)V);
-#pragma unroll
-      for (int c = 0; c < CC; ++c) coef[c] = cf;
+      coef0 = (float)(g * (double)__ldg(p.bare_weight + b * p.weight_stride) / (double)V);
     } else {  // kModeCE
       double den = 0.0;
       for (int c = 0; c < nc; ++c) den += (double)__ldg(p.class_w + c) * __ldg(p.class_counts + c);
@@ -222,75 +261,156 @@ __global__ void __launch_bounds__(kThreads) loss_kernel(const LossParams p) {
   }
 
   const int64_t u0 = p.units * chunk / p.chunks, u1 = p.units * (chunk + 1) / p.chunks;
-  const LT* __restrict__ zb = reinterpret_cast<const LT*>(p.logits) + (int64_t)b * nc * V;
-  LT* __restrict__ gb = reinterpret_cast<LT*>(p.dlogits) + (int64_t)b * nc * V;
-  const TT* __restrict__ tb = reinterpret_cast<const TT*>(p.target) + (int64_t)b * V;
-  const TT* __restrict__ db = p.dice_target ? reinterpret_cast<const TT*>(p.dice_target) + (int64_t)b * V : nullptr;
+  // per-thread streaming pointers, advanced by one CTA step (kThreads * VEC voxels) per iteration
+  const int64_t v_first = (u0 + threadIdx.x) * VEC;
+  const LT* __restrict__ pz = reinterpret_cast<const LT*>(p.logits) + (int64_t)b * nc * V + v_first;
+  LT* __restrict__ pg = reinterpret_cast<LT*>(p.dlogits) + (int64_t)b * nc * V + v_first;
+  const TT* __restrict__ pt = reinterpret_cast<const TT*>(p.target) + (int64_t)b * V + v_first;
+  const TT* __restrict__ pd = DICE ? reinterpret_cast<const TT*>(p.dice_target) + (int64_t)b * V + v_first : nullptr;
+  constexpr int kStep = kThreads * VEC;
+  // C == 2 without a separate Dice target: all label / true-positive counts come from one packed
+  // histogram over (t, argmax) with four 8-bit fields, flushed before a field can overflow
+  constexpr bool PACKED = STATS && C == 2 && !DICE;
+  constexpr int kFlushIters = 252 / VEC;
 
   float nll_c[CC];
   int lab_c[CC], pred_c[CC], tp_c[CC];
 #pragma unroll
   for (int c = 0; c < CC; ++c) nll_c[c] = 0.f, lab_c[c] = 0, pred_c[c] = 0, tp_c[c] = 0;
+  int hist_w[4] = {0, 0, 0, 0};
 
-  for (int64_t u = u0 + threadIdx.x; u < u1; u += kThreads) {
-    const int64_t v = u * VEC;
-    float z[CC][VEC];
-    int t[VEC], td[VEC];
+  int seen = 0;  // voxels this thread processed (-> predicted-class-0 count)
+  int64_t u = u0 + threadIdx.x;
+  while (u < u1) {
+    unsigned hist = 0u;
+    int64_t u_stop = u + (int64_t)kFlushIters * kThreads;
+    if (!PACKED || u_stop > u1) u_stop = u1;
+    for (; u < u_stop; u += kThreads, pz += kStep, pg += kStep, pt += kStep, pd += DICE ? kStep : 0) {
+      seen += VEC;
+      float z[CC][VEC];
+      int t[VEC], td[VEC];
 #pragma unroll
-    for (int c = 0; c < CC; ++c)
-      if (c < nc) Logit<LT>::template load<VEC>(zb + (int64_t)c * V + v, z[c]);
-    Label<TT>::template load<VEC>(tb + v, t);
-    if (STATS && db) {
-      Label<TT>::template load<VEC>(db + v, td);
-    } else {
+      for (int c = 0; c < CC; ++c)
+        if (c < nc) Logit<LT>::template load<VEC>(pz + (int64_t)c * V, z[c]);
+      Label<TT>::template load<VEC>(pt, t);
+      if constexpr (STATS && DICE) {
+        Label<TT>::template load<VEC>(pd, td);
+      } else {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) td[i] = t[i];
-    }
-    float gr[CC][VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      float m = z[0][i];
-      int am = 0;
-#pragma unroll
-      for (int c = 1; c < CC; ++c)
-        if (c < nc && z[c][i] > m) m = z[c][i], am = c;  // strict > : first maximum wins (:751)
-      float e[CC], sum = 0.f, zt = 0.f, cf = 0.f;
-#pragma unroll
-      for (int c = 0; c < CC; ++c) {
-        if (c < nc) {
-          e[c] = expf(z[c][i] - m);
-          sum += e[c];
-          if (t[i] == c) zt = z[c][i], cf = coef[c];
-        }
+        for (int i = 0; i < VEC; ++i) td[i] = t[i];
       }
-      const bool valid = t[i] >= 0 && t[i] < nc;  // anything else (e.g. torch's ignore_index) adds nothing
-      if (STATS) {
-        const float nll = valid ? (logf(sum) + (m - zt)) : 0.f;  // -log softmax(z)[t]  (:738)
+      float gr[CC][VEC];
+      constexpr float kLog2e = 1.4426950408889634f;
 #pragma unroll
-        for (int c = 0; c < CC; ++c) {
-          if (c < nc) {
-            nll_c[c] += (t[i] == c) ? nll : 0.f;
-            lab_c[c] += (t[i] == c) ? 1 : 0;
-            pred_c[c] += (am == c) ? 1 : 0;
-            tp_c[c] += (am == c && td[i] == c) ? 1 : 0;
+      for (int i = 0; i < VEC; ++i) {
+        const int ti = t[i];
+        const bool valid = (unsigned)ti < (unsigned)nc;  // anything else (e.g. torch's ignore_index) adds nothing
+        if constexpr (C == 2) {
+          // ---- binary fast path: softplus / sigmoid of d = z1 - z0 ------------------------------------
+          const float d = z[1][i] - z[0][i];
+          const bool am1 = d > 0.f;  // strict > : first maximum wins (:751)
+          const float a = fabsf(d);
+          const float e = ex2_approx(a * -kLog2e);  // exp(-|d|) in (0, 1]
+          const float inv = rcp_approx(1.0f + e);   // softmax of the maximal class
+          const bool t1 = ti == 1;
+          if (STATS) {
+            // log(1 + e) = 2 atanh(u), u = e / (2 + e) <= 1/3; odd series with a fitted tail
+            // (|rel err| < 2e-7 in fp32, relative -- confident voxels keep their tiny loss)
+            const float uu = e * rcp_approx(2.0f + e);
+            const float w = uu * uu;
+            float q = 1.3433776651e-01f;
+            q = fmaf(q, w, 1.4116977575e-01f);
+            q = fmaf(q, w, 2.0003835452e-01f);
+            q = fmaf(q, w, 3.3333319833e-01f);
+            const float u2 = uu + uu;
+            const float lse = fmaf(u2 * w, q, u2);
+            const float nll = lse + ((t1 != am1) ? a : 0.f);  // -log softmax(z)[t]  (:738)
+            nll_c[0] += (ti == 0) ? nll : 0.f;
+            nll_c[1] += t1 ? nll : 0.f;
+            pred_c[1] += am1 ? 1 : 0;
+            if constexpr (PACKED) {
+              const unsigned sh = (unsigned)ti * 8u + (am1 ? 16u : 0u);
+              hist += valid ? (1u << (sh & 31u)) : 0u;
+            } else {
+              lab_c[0] += (ti == 0) ? 1 : 0;
+              lab_c[1] += t1 ? 1 : 0;
+              tp_c[0] += (!am1 && td[i] == 0) ? 1 : 0;
+              tp_c[1] += (am1 && td[i] == 1) ? 1 : 0;
+            }
+          }
+          if (GRAD) {
+            float cf = uniform_coef ? coef0 : (t1 ? coef[1] : coef[0]);
+            cf = valid ? cf : 0.f;
+            const float p1 = am1 ? inv : e * inv;
+            const float g1 = fmaf(p1, cf, t1 ? -cf : 0.f);
+            gr[1][i] = g1;
+            gr[0][i] = -g1;
+          }
+        } else {
+          // ---- general class count -------------------------------------------------------------------
+          float m = z[0][i];
+          int am = 0;
+#pragma unroll
+          for (int c = 1; c < CC; ++c)
+            if (c < nc && z[c][i] > m) m = z[c][i], am = c;  // strict > : first maximum wins (:751)
+          float e[CC];
+          float rest = 0.f, zt = m;  // rest = sum of the non-maximal exp(z_c - max)
+#pragma unroll
+          for (int c = 0; c < CC; ++c) {
+            if (c < nc) {
+              e[c] = ex2_approx((z[c][i] - m) * kLog2e);  // exactly 1 for the maximum
+              rest += (c == am) ? 0.f : e[c];
+              zt = (ti == c) ? z[c][i] : zt;
+            }
+          }
+          if (STATS) {
+            const float nll = log1p_pos(rest) + (m - zt);  // -log softmax(z)[t]  (:738); only added where t == c
+#pragma unroll
+            for (int c = 0; c < CC; ++c) {
+              if (c < nc) {
+                nll_c[c] += (ti == c) ? nll : 0.f;
+                lab_c[c] += (ti == c) ? 1 : 0;
+                if (c > 0) pred_c[c] += (am == c) ? 1 : 0;  // class 0 = voxels seen - the others
+                tp_c[c] += (am == c && td[i] == c) ? 1 : 0;
+              }
+            }
+          }
+          if (GRAD) {
+            float cf = 0.f;
+            if (uniform_coef) {
+              cf = valid ? coef0 : 0.f;
+            } else {
+#pragma unroll
+              for (int c = 0; c < CC; ++c)
+                if (c < nc) cf = (ti == c) ? coef[c] : cf;
+            }
+            const float cinv = cf * rcp_approx(1.0f + rest);
+#pragma unroll
+            for (int c = 0; c < CC; ++c)
+              if (c < nc) gr[c][i] = fmaf(e[c], cinv, (ti == c) ? -cf : 0.f);
           }
         }
       }
       if (GRAD) {
-        const float inv = __frcp_rn(sum);
 #pragma unroll
         for (int c = 0; c < CC; ++c)
-          if (c < nc) gr[c][i] = cf * (e[c] * inv - ((t[i] == c) ? 1.f : 0.f));
+          if (c < nc) Logit<LT>::template store<VEC>(pg + (int64_t)c * V, gr[c]);
       }
     }
-    if (GRAD) {
+    if constexpr (PACKED) {
 #pragma unroll
-      for (int c = 0; c < CC; ++c)
-        if (c < nc) Logit<LT>::template store<VEC>(gb + (int64_t)c * V + v, gr[c]);
+      for (int k = 0; k < 4; ++k) hist_w[k] += (int)((hist >> (8 * k)) & 0xffu);
     }
+  }
+  if constexpr (PACKED) {  // fields: [t=0,am=0] [t=1,am=0] [t=0,am=1] [t=1,am=1]
+    lab_c[0] = hist_w[0] + hist_w[2], lab_c[1] = hist_w[1] + hist_w[3];
+    tp_c[0] = hist_w[0], tp_c[1] = hist_w[3];
   }
 
   if (STATS) {
+    pred_c[0] = seen;
+#pragma unroll
+    for (int c = 1; c < CC; ++c) pred_c[0] -= pred_c[c];
     double vals[CC * 4];
 #pragma unroll
     for (int c = 0; c < CC; ++c) {

@@ -8,12 +8,16 @@ namespace ds {
 template <typename LT, typename TT, int C, int VEC>
 int launch_cfg(const LossParams& p, bool grad, bool stats, cudaStream_t stream) {
   const dim3 grid((unsigned)(p.B_local * p.chunks));
-  if (grad && stats)
-    loss_kernel<LT, TT, C, VEC, true, true><<<grid, kThreads, 0, stream>>>(p);
-  else if (stats)
-    loss_kernel<LT, TT, C, VEC, false, true><<<grid, kThreads, 0, stream>>>(p);
-  else
-    loss_kernel<LT, TT, C, VEC, true, false><<<grid, kThreads, 0, stream>>>(p);
+  const bool dice = stats && p.dice_target != nullptr;
+  if (grad && stats) {
+    if (dice) loss_kernel<LT, TT, C, VEC, true, true, true><<<grid, kThreads, 0, stream>>>(p);
+    else loss_kernel<LT, TT, C, VEC, true, true, false><<<grid, kThreads, 0, stream>>>(p);
+  } else if (stats) {
+    if (dice) loss_kernel<LT, TT, C, VEC, false, true, true><<<grid, kThreads, 0, stream>>>(p);
+    else loss_kernel<LT, TT, C, VEC, false, true, false><<<grid, kThreads, 0, stream>>>(p);
+  } else {
+    loss_kernel<LT, TT, C, VEC, true, false, false><<<grid, kThreads, 0, stream>>>(p);
+  }
   count_launch();
   return check_launch("loss_kernel");
 }

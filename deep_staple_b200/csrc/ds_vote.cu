@@ -22,6 +22,7 @@ template <typename LT, bool VECP>
 struct VoteIn;
 template <>
 struct VoteIn<int64_t, true> {
+  static constexpr bool kBinaryPath = false;  // 8 B per voxel-candidate: already HBM-bound, keep registers for loads
   static constexpr int VPT = 4;  // 2 x 16 B
   struct Raw {
     uint4 a, b;
@@ -33,18 +34,33 @@ struct VoteIn<int64_t, true> {
     f[2] = __ll2float_rn((long long)(((unsigned long long)r.b.y << 32) | r.b.x));
     f[3] = __ll2float_rn((long long)(((unsigned long long)r.b.w << 32) | r.b.z));
   }
+  static __device__ __forceinline__ uint32_t nonbinary_bits(const Raw& r) {
+    return (r.a.y | r.a.w | r.b.y | r.b.w) | ((r.a.x | r.a.z | r.b.x | r.b.z) & ~1u);
+  }
+  static __device__ __forceinline__ void add_binary(const Raw& r, float w, float (&acc)[VPT]) {
+    if (r.a.x) acc[0] = __fadd_rn(acc[0], w);
+    if (r.a.z) acc[1] = __fadd_rn(acc[1], w);
+    if (r.b.x) acc[2] = __fadd_rn(acc[2], w);
+    if (r.b.z) acc[3] = __fadd_rn(acc[3], w);
+  }
 };
 template <>
 struct VoteIn<int64_t, false> {
+  static constexpr bool kBinaryPath = false;
   static constexpr int VPT = 1;
   struct Raw {
     long long a;
   };
   static __device__ __forceinline__ Raw load(const int64_t* p) { return {__ldg((const long long*)p)}; }
   static __device__ __forceinline__ void to_float(const Raw& r, float (&f)[VPT]) { f[0] = __ll2float_rn(r.a); }
+  static __device__ __forceinline__ uint32_t nonbinary_bits(const Raw& r) { return ((unsigned long long)r.a > 1ull) ? 1u : 0u; }
+  static __device__ __forceinline__ void add_binary(const Raw& r, float w, float (&acc)[VPT]) {
+    if (r.a) acc[0] = __fadd_rn(acc[0], w);
+  }
 };
 template <>
 struct VoteIn<uint8_t, true> {
+  static constexpr bool kBinaryPath = true;  // 1 B per voxel-candidate: instruction issue is the limit
   static constexpr int VPT = 16;  // 1 x 16 B
   struct Raw {
     uint4 a;
@@ -58,15 +74,32 @@ struct VoteIn<uint8_t, true> {
       for (int j = 0; j < 4; ++j) f[4 * i + j] = (float)((w[i] >> (8 * j)) & 0xffu);
     }
   }
+  static __device__ __forceinline__ uint32_t nonbinary_bits(const Raw& r) {
+    return (r.a.x | r.a.y | r.a.z | r.a.w) & 0xfefefefeu;
+  }
+  static __device__ __forceinline__ void add_binary(const Raw& r, float w, float (&acc)[VPT]) {
+    const uint32_t wd[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (wd[i] & (1u << (8 * j))) acc[4 * i + j] = __fadd_rn(acc[4 * i + j], w);
+    }
+  }
 };
 template <>
 struct VoteIn<uint8_t, false> {
+  static constexpr bool kBinaryPath = false;
   static constexpr int VPT = 1;
   struct Raw {
     uint8_t a;
   };
   static __device__ __forceinline__ Raw load(const uint8_t* p) { return {__ldg(p)}; }
   static __device__ __forceinline__ void to_float(const Raw& r, float (&f)[VPT]) { f[0] = (float)r.a; }
+  static __device__ __forceinline__ uint32_t nonbinary_bits(const Raw& r) { return r.a & 0xfeu; }
+  static __device__ __forceinline__ void add_binary(const Raw& r, float w, float (&acc)[VPT]) {
+    if (r.a) acc[0] = __fadd_rn(acc[0], w);
+  }
 };
 
 template <typename OT, int VPT>
@@ -209,15 +242,31 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
           for (int j = 0; j < kBatch; ++j)
             if (nb + j < nn) raw[j] = In::load(pl + (int64_t)j * V);
           pl += (int64_t)kBatch * V;
+          // {0,1} labels (the reference's data): float(label) * w is exactly w or +0, so the vote is a
+          // predicated add -- two instructions per voxel-candidate instead of convert + mul + add.
+          // Any other label value in this batch of planes sends the thread down the general path.
+          uint32_t nonbin = 1u;
+          if constexpr (In::kBinaryPath) {
+            nonbin = 0u;
 #pragma unroll
-          for (int j = 0; j < kBatch; ++j) {
-            if (nb + j < nn) {
-              const float w = s_w[nb + j];
-              float f[VPT];
-              In::to_float(raw[j], f);
-              // product and sum rounded separately, like ATen's mul followed by sum (no FMA)
+            for (int j = 0; j < kBatch; ++j)
+              if (nb + j < nn) nonbin |= In::nonbinary_bits(raw[j]);
+          }
+          if (In::kBinaryPath && nonbin == 0u) {
 #pragma unroll
-              for (int i = 0; i < VPT; ++i) acc[0][i] = __fadd_rn(acc[0][i], __fmul_rn(f[i], w));
+            for (int j = 0; j < kBatch; ++j)
+              if (nb + j < nn) In::add_binary(raw[j], s_w[nb + j], acc[0]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+              if (nb + j < nn) {
+                const float w = s_w[nb + j];
+                float f[VPT];
+                In::to_float(raw[j], f);
+                // product and sum rounded separately, like ATen's mul followed by sum (no FMA)
+#pragma unroll
+                for (int i = 0; i < VPT; ++i) acc[0][i] = __fadd_rn(acc[0][i], __fmul_rn(f[i], w));
+              }
             }
           }
           // ATen cascade: after every full block of 16 rows fold level 0 into level 1, after
