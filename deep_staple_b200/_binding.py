@@ -12,7 +12,9 @@ from ctypes import c_char_p, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libdeep_staple_b200.so")
+# DS_LIB_PATH: kernel-tuning experiments load an alternative build of the SAME library (build.py --variant)
+_LIB_PATH = os.environ.get("DS_LIB_PATH") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "_lib", "libdeep_staple_b200.so")
 
 # ds_dtype (include/deep_staple_b200.h)
 DS_F32, DS_F16, DS_BF16, DS_I64, DS_U8 = 0, 1, 2, 3, 4

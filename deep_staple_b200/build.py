@@ -72,6 +72,31 @@ def _compile(src: str, verbose: bool) -> str:
     return obj
 
 
+def build_variant(name: str, extra_flags) -> str:
+    """Experiment helper: build the library with extra nvcc flags (e.g. -DDS_LOSS_MIN_BLOCKS=5) into
+    build/alt/<name>/; select it at run time with DS_LIB_PATH (see _binding.py)."""
+    out_dir = os.path.join(ROOT, "build", "alt", name)
+    os.makedirs(out_dir, exist_ok=True)
+    objs = []
+
+    def one(src):
+        obj = os.path.join(out_dir, os.path.basename(src)[:-3] + ".o")
+        res = subprocess.run([_nvcc(), *NVCC_FLAGS, *extra_flags, *INCLUDE_FLAGS, "-c", src, "-o", obj],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(res.stderr)
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+        objs = list(pool.map(one, sources()))
+    lib = os.path.join(out_dir, "libdeep_staple_b200.so")
+    res = subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(res.stderr)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ for sm_100a and link the shared library.  Returns its path."""
     if not force and is_current():
@@ -91,4 +116,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

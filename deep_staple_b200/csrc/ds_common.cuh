@@ -55,7 +55,54 @@ __device__ __forceinline__ void stg_stream4(void* p, uint32_t v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// logits: load VEC consecutive values of one class plane as fp32 / store VEC gradients
+// raw register image of BYTES consecutive bytes of global memory (load now, decode later: lets a
+// kernel keep the NEXT step's loads in flight while it computes on the current step)
+// ---------------------------------------------------------------------------------------------
+template <int BYTES>
+struct Raw {
+  uint32_t w[(BYTES + 3) / 4];
+};
+
+template <int BYTES>
+__device__ __forceinline__ void load_raw(const void* p, Raw<BYTES>& r) {
+  if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < BYTES / 16; ++i) {
+      const uint4 v = ldg_stream16(reinterpret_cast<const char*>(p) + 16 * i);
+      r.w[4 * i] = v.x, r.w[4 * i + 1] = v.y, r.w[4 * i + 2] = v.z, r.w[4 * i + 3] = v.w;
+    }
+  } else if constexpr (BYTES == 8) {
+    const uint2 v = ldg_stream8(p);
+    r.w[0] = v.x, r.w[1] = v.y;
+  } else if constexpr (BYTES == 4) {
+    r.w[0] = ldg_stream4(p);
+  } else if constexpr (BYTES == 2) {
+    r.w[0] = __ldg(reinterpret_cast<const unsigned short*>(p));
+  } else {
+    static_assert(BYTES == 1, "unsupported raw width");
+    r.w[0] = __ldg(reinterpret_cast<const unsigned char*>(p));
+  }
+}
+
+template <int BYTES>
+__device__ __forceinline__ void store_raw(void* p, const Raw<BYTES>& r) {
+  if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < BYTES / 16; ++i)
+      stg_stream16(reinterpret_cast<char*>(p) + 16 * i, make_uint4(r.w[4 * i], r.w[4 * i + 1], r.w[4 * i + 2], r.w[4 * i + 3]));
+  } else if constexpr (BYTES == 8) {
+    stg_stream8(p, make_uint2(r.w[0], r.w[1]));
+  } else if constexpr (BYTES == 4) {
+    stg_stream4(p, r.w[0]);
+  } else if constexpr (BYTES == 2) {
+    *reinterpret_cast<unsigned short*>(p) = (unsigned short)r.w[0];
+  } else {
+    *reinterpret_cast<unsigned char*>(p) = (unsigned char)r.w[0];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// logits: VEC consecutive values of one class plane <-> fp32
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 struct Logit;
@@ -66,25 +113,14 @@ struct Logit<float> {
   static __device__ __forceinline__ float to_f32(float v) { return v; }
   static __device__ __forceinline__ float from_f32(float v) { return v; }
   template <int VEC>
-  static __device__ __forceinline__ void load(const float* p, float (&z)[VEC]) {
-    if constexpr (VEC == 4) {
-      uint4 r = ldg_stream16(p);
-      z[0] = __uint_as_float(r.x), z[1] = __uint_as_float(r.y), z[2] = __uint_as_float(r.z),
-      z[3] = __uint_as_float(r.w);
-    } else {
+  static __device__ __forceinline__ void decode(const Raw<4 * VEC>& r, float (&z)[VEC]) {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) z[i] = __ldg(p + i);
-    }
+    for (int i = 0; i < VEC; ++i) z[i] = __uint_as_float(r.w[i]);
   }
   template <int VEC>
-  static __device__ __forceinline__ void store(float* p, const float (&g)[VEC]) {
-    if constexpr (VEC == 4) {
-      stg_stream16(p, make_uint4(__float_as_uint(g[0]), __float_as_uint(g[1]), __float_as_uint(g[2]),
-                                 __float_as_uint(g[3])));
-    } else {
+  static __device__ __forceinline__ void encode(const float (&g)[VEC], Raw<4 * VEC>& r) {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) p[i] = g[i];
-    }
+    for (int i = 0; i < VEC; ++i) r.w[i] = __float_as_uint(g[i]);
   }
 };
 
@@ -93,37 +129,29 @@ struct Logit<__half> {
   static constexpr int kDtype = DS_F16;
   static __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
   static __device__ __forceinline__ __half from_f32(float v) { return __float2half_rn(v); }
-  static __device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
-    __half2 h = *reinterpret_cast<__half2*>(&w);
-    float2 f = __half22float2(h);
-    a = f.x, b = f.y;
-  }
-  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
   template <int VEC>
-  static __device__ __forceinline__ void load(const __half* p, float (&z)[VEC]) {
-    if constexpr (VEC == 8) {
-      uint4 r = ldg_stream16(p);
-      unpack2(r.x, z[0], z[1]), unpack2(r.y, z[2], z[3]), unpack2(r.z, z[4], z[5]), unpack2(r.w, z[6], z[7]);
-    } else if constexpr (VEC == 4) {
-      uint2 r = ldg_stream8(p);
-      unpack2(r.x, z[0], z[1]), unpack2(r.y, z[2], z[3]);
+  static __device__ __forceinline__ void decode(const Raw<2 * VEC>& r, float (&z)[VEC]) {
+    if constexpr (VEC == 1) {
+      z[0] = __half2float(__ushort_as_half((unsigned short)r.w[0]));
     } else {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) z[i] = __half2float(p[i]);
+      for (int i = 0; i < VEC / 2; ++i) {
+        uint32_t w = r.w[i];
+        const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+        z[2 * i] = f.x, z[2 * i + 1] = f.y;
+      }
     }
   }
   template <int VEC>
-  static __device__ __forceinline__ void store(__half* p, const float (&g)[VEC]) {
-    if constexpr (VEC == 8) {
-      stg_stream16(p, make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7])));
-    } else if constexpr (VEC == 4) {
-      stg_stream8(p, make_uint2(pack2(g[0], g[1]), pack2(g[2], g[3])));
+  static __device__ __forceinline__ void encode(const float (&g)[VEC], Raw<2 * VEC>& r) {
+    if constexpr (VEC == 1) {
+      r.w[0] = __half_as_ushort(__float2half_rn(g[0]));
     } else {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) p[i] = __float2half_rn(g[i]);
+      for (int i = 0; i < VEC / 2; ++i) {
+        __half2 h = __floats2half2_rn(g[2 * i], g[2 * i + 1]);
+        r.w[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
     }
   }
 };
@@ -133,42 +161,34 @@ struct Logit<__nv_bfloat16> {
   static constexpr int kDtype = DS_BF16;
   static __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
   static __device__ __forceinline__ __nv_bfloat16 from_f32(float v) { return __float2bfloat16_rn(v); }
-  static __device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
-    a = __uint_as_float(w << 16);  // bf16 is the upper half of an fp32
-    b = __uint_as_float(w & 0xffff0000u);
-  }
-  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
   template <int VEC>
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&z)[VEC]) {
-    if constexpr (VEC == 8) {
-      uint4 r = ldg_stream16(p);
-      unpack2(r.x, z[0], z[1]), unpack2(r.y, z[2], z[3]), unpack2(r.z, z[4], z[5]), unpack2(r.w, z[6], z[7]);
-    } else if constexpr (VEC == 4) {
-      uint2 r = ldg_stream8(p);
-      unpack2(r.x, z[0], z[1]), unpack2(r.y, z[2], z[3]);
+  static __device__ __forceinline__ void decode(const Raw<2 * VEC>& r, float (&z)[VEC]) {
+    if constexpr (VEC == 1) {
+      z[0] = __uint_as_float(r.w[0] << 16);  // bf16 is the upper half of an fp32
     } else {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) z[i] = __bfloat162float(p[i]);
+      for (int i = 0; i < VEC / 2; ++i) {
+        z[2 * i] = __uint_as_float(r.w[i] << 16);
+        z[2 * i + 1] = __uint_as_float(r.w[i] & 0xffff0000u);
+      }
     }
   }
   template <int VEC>
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&g)[VEC]) {
-    if constexpr (VEC == 8) {
-      stg_stream16(p, make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7])));
-    } else if constexpr (VEC == 4) {
-      stg_stream8(p, make_uint2(pack2(g[0], g[1]), pack2(g[2], g[3])));
+  static __device__ __forceinline__ void encode(const float (&g)[VEC], Raw<2 * VEC>& r) {
+    if constexpr (VEC == 1) {
+      r.w[0] = __bfloat16_as_ushort(__float2bfloat16_rn(g[0]));
     } else {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) p[i] = __float2bfloat16_rn(g[i]);
+      for (int i = 0; i < VEC / 2; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(g[2 * i], g[2 * i + 1]);
+        r.w[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
     }
   }
 };
 
 // ---------------------------------------------------------------------------------------------
-// labels: load VEC consecutive labels as int.  int64: low word OR high word -- any negative value
+// labels: VEC consecutive labels -> int.  int64: low word OR high word -- any negative value
 // (torch's ignore_index = -100) becomes negative = "no class"; values >= 2^32 are undefined
 // behaviour in the reference too (device-side assert in torch)
 // ---------------------------------------------------------------------------------------------
@@ -178,22 +198,10 @@ struct Label;
 template <>
 struct Label<int64_t> {
   static constexpr int kDtype = DS_I64;
-  static __device__ __forceinline__ int narrow(uint32_t lo, uint32_t hi) { return (int)(lo | hi); }
   template <int VEC>
-  static __device__ __forceinline__ void load(const int64_t* p, int (&t)[VEC]) {
-    if constexpr (VEC % 2 == 0) {
+  static __device__ __forceinline__ void decode(const Raw<8 * VEC>& r, int (&t)[VEC]) {
 #pragma unroll
-      for (int i = 0; i < VEC / 2; ++i) {
-        uint4 r = ldg_stream16(p + 2 * i);
-        t[2 * i] = narrow(r.x, r.y), t[2 * i + 1] = narrow(r.z, r.w);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        long long v = __ldg(reinterpret_cast<const long long*>(p) + i);
-        t[i] = narrow((uint32_t)v, (uint32_t)((unsigned long long)v >> 32));
-      }
-    }
+    for (int i = 0; i < VEC; ++i) t[i] = (int)(r.w[2 * i] | r.w[2 * i + 1]);
   }
 };
 
@@ -201,21 +209,25 @@ template <>
 struct Label<uint8_t> {
   static constexpr int kDtype = DS_U8;
   template <int VEC>
-  static __device__ __forceinline__ void load(const uint8_t* p, int (&t)[VEC]) {
-    if constexpr (VEC == 8) {
-      uint2 r = ldg_stream8(p);
+  static __device__ __forceinline__ void decode(const Raw<VEC>& r, int (&t)[VEC]) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) t[i] = (r.x >> (8 * i)) & 0xff, t[4 + i] = (r.y >> (8 * i)) & 0xff;
-    } else if constexpr (VEC == 4) {
-      uint32_t r = ldg_stream4(p);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) t[i] = (r >> (8 * i)) & 0xff;
-    } else {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) t[i] = __ldg(p + i);
-    }
+    for (int i = 0; i < VEC; ++i) t[i] = (int)((r.w[i / 4] >> (8 * (i % 4))) & 0xffu);
   }
 };
+
+// load + decode in one go (kernels that do not pipeline their loads)
+template <typename LT, int VEC>
+__device__ __forceinline__ void load_logits(const LT* p, float (&z)[VEC]) {
+  Raw<(int)sizeof(LT) * VEC> r;
+  load_raw(p, r);
+  Logit<LT>::template decode<VEC>(r, z);
+}
+template <typename TT, int VEC>
+__device__ __forceinline__ void load_labels(const TT* p, int (&t)[VEC]) {
+  Raw<(int)sizeof(TT) * VEC> r;
+  load_raw(p, r);
+  Label<TT>::template decode<VEC>(r, t);
+}
 
 // ---------------------------------------------------------------------------------------------
 // reductions (fixed order -> run-to-run deterministic)

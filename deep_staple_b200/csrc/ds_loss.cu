@@ -12,47 +12,58 @@ extern template int launch_loss_typed<__nv_bfloat16>(const LossParams&, int, boo
 
 namespace {
 
-constexpr size_t kTicketAlign = 16;
-
-size_t ticket_bytes(int64_t B_local) {
-  const size_t raw = sizeof(unsigned int) * (size_t)(1 + B_local);
-  return (raw + kTicketAlign - 1) / kTicketAlign * kTicketAlign;
-}
-
 bool aligned16(const void* p) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
-int logit_bytes(int dt) { return dt == DS_F32 ? 4 : 2; }
+size_t header_bytes() { return sizeof(unsigned int) * kWsCounters; }
 
-// chunks per instance: about one full wave of resident CTAs (or DS_LOSS_WAVES of them), every CTA
-// with at least one full step, never more CTAs than the workspace was sized for
-int pick_chunks(int64_t B_local, int64_t units) {
-  const int sms = sm_count();
-  const int per_sm = env_int("DS_LOSS_CTAS_PER_SM", 4), waves = env_int("DS_LOSS_WAVES", 2);
-  int64_t want = ((int64_t)sms * per_sm * waves + B_local - 1) / B_local;
-  int64_t cap = (units + kThreads - 1) / kThreads;
-  const int64_t ws_cap = kMaxLossCtas / B_local;
-  if (cap > ws_cap) cap = ws_cap;
-  if (want > cap) want = cap;
+// Launch geometry of the persistent kernels: warp steps of 32 units; DS_LOSS_CTAS_PER_SM resident CTAs per SM (never more CTAs than there are
+// groups of kWarps tiles); fixed-point scale of the loss sums sized so that V voxels x 2^10 cannot
+// overflow 63 bits.
+int setup_tiles(LossParams& p, const char* who, bool stats) {
+  (void)who;
+  p.steps_per_inst = (p.units + 31) / 32;
+  p.n_steps = p.steps_per_inst * p.B_local;
+  const int per_sm = env_int("DS_LOSS_CTAS_PER_SM", loss_min_blocks(p.units == p.V ? 0 : p.C, p.units * 8 == p.V ? 8 : 4));
+  int64_t grid = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
+  const int64_t need = (p.n_steps + kWarps - 1) / kWarps;
+  if (grid > need) grid = need;
+  p.grid = (int)(grid < 1 ? 1 : grid);
+  // groups: the largest divisor of the grid that does not exceed the number of instances, so every
+  // group is a whole number of CTAs and a warp meets at most ~2 instance boundaries.  Kernels
+  // without statistics have nothing to flush: one group, one front.
+  int want = stats ? (int)(p.B_local < p.grid ? p.B_local : p.grid) : 1;
+  want = env_int("DS_LOSS_GROUPS", want);
   if (want < 1) want = 1;
-  return (int)want;
+  if (want > p.grid) want = p.grid;
+  p.groups = 1;
+  for (int d = want; d >= 1; --d)
+    if (p.grid % d == 0) {
+      p.groups = d;
+      break;
+    }
+  int bits_v = 0;
+  while (((int64_t)1 << bits_v) < p.V) ++bits_v;
+  int e = 62 - bits_v - 10;
+  if (e > 40) e = 40;
+  if (e < 0) e = 0;
+  p.nll_scale = (double)((int64_t)1 << e);
+  return 0;
 }
 
-int setup_geometry(LossParams& p, int logit_dtype, int target_dtype, bool* vec_out) {
+int setup_geometry(LossParams& p, int logit_dtype, bool* vec_out, const char* who, bool stats) {
   const int C = p.C;
   const int W = (logit_dtype == DS_F32) ? 4 : (C <= 4 ? 8 : 4);
   bool vec = (p.V % W == 0) && aligned16(p.logits) && aligned16(p.dlogits) && aligned16(p.target) &&
              aligned16(p.dice_target);
   if (env_int("DS_FORCE_SCALAR", 0)) vec = false;
   p.units = vec ? p.V / W : p.V;
-  p.chunks = pick_chunks(p.B_local, p.units);
   *vec_out = vec;
-  (void)target_dtype;
-  return 0;
+  return setup_tiles(p, who, stats);
 }
 
 int launch_loss(LossParams& p, int logit_dtype, int target_dtype, bool grad, bool stats, cudaStream_t stream) {
   bool vec = false;
-  setup_geometry(p, logit_dtype, target_dtype, &vec);
+  if (int rc = setup_geometry(p, logit_dtype, &vec, "loss_kernel", stats)) return rc;
   switch (logit_dtype) {
     case DS_F32: return launch_loss_typed<float>(p, target_dtype, grad, stats, vec, stream);
     case DS_F16: return launch_loss_typed<__half>(p, target_dtype, grad, stats, vec, stream);
@@ -66,8 +77,8 @@ int carve_workspace(LossParams& p, void* workspace, size_t workspace_bytes, cons
   const size_t need = ds_dp_loss_workspace_bytes(p.B_local, p.C);
   if (workspace_bytes < need)
     return fail(DS_ERR_WORKSPACE, "%s: workspace has %zu bytes, %zu needed", who, workspace_bytes, need);
-  p.tickets = reinterpret_cast<unsigned int*>(workspace);
-  p.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + ticket_bytes(p.B_local));
+  p.counters = reinterpret_cast<unsigned int*>(workspace);
+  p.acc = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + header_bytes());
   return 0;
 }
 
@@ -80,7 +91,6 @@ int check_common(const char* who, const void* logits, int logit_dtype, const voi
     return fail(DS_ERR_DTYPE, "%s: target must be DS_I64 or DS_U8 (got %d)", who, target_dtype);
   if (B <= 0 || V <= 0) return fail(DS_ERR_SHAPE, "%s: B and V must be positive", who);
   if (C < 2 || C > DS_MAX_CLASSES) return fail(DS_ERR_SHAPE, "%s: C=%lld outside [2, %d]", who, (long long)C, DS_MAX_CLASSES);
-  if (B > 0x7fffffffLL / kMaxLossCtas) return fail(DS_ERR_SHAPE, "%s: B=%lld too large", who, (long long)B);
   return ds_device_check();
 }
 
@@ -99,25 +109,36 @@ __global__ void __launch_bounds__(kThreads) rescale_kernel(T* __restrict__ x, in
     x[i] = Logit<T>::from_f32(Logit<T>::to_f32(x[i]) * r);
 }
 
-// label maps only: per instance and class  #(target==c), #(pred==c), #(pred==c && target==c)
+// label maps only: per instance and class  #(target==c), #(pred==c), #(pred==c && target==c).
+// Same persistent warp-tile schedule and exact integer accumulation as the loss kernel.
 template <typename TT, int VEC>
 __global__ void __launch_bounds__(kThreads) label_stats_kernel(const LossParams p) {
   constexpr int CC = DS_MAX_CLASSES;
-  __shared__ double s_red[kWarps * 32];
   __shared__ double s_scratch[kWarps + 1];
-  const int b = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
+  const int lane = threadIdx.x & 31;
   const int nc = p.C;
-  const TT* __restrict__ pb = reinterpret_cast<const TT*>(p.logits) + (int64_t)b * p.V;  // `logits` carries pred
-  const TT* __restrict__ tb = p.target ? reinterpret_cast<const TT*>(p.target) + (int64_t)b * p.V : nullptr;
+  long long nll_fix[CC];
   int lab_c[CC], pred_c[CC], tp_c[CC];
 #pragma unroll
-  for (int c = 0; c < CC; ++c) lab_c[c] = 0, pred_c[c] = 0, tp_c[c] = 0;
-  const int64_t u0 = p.units * chunk / p.chunks, u1 = p.units * (chunk + 1) / p.chunks;
-  for (int64_t u = u0 + threadIdx.x; u < u1; u += kThreads) {
+  for (int c = 0; c < CC; ++c) nll_fix[c] = 0, lab_c[c] = 0, pred_c[c] = 0, tp_c[c] = 0;
+  const StepWalk walk(p);
+  int cur_b = -1;
+  int b = walk.b0;
+  int64_t s_in = walk.s_in0;
+  for (int64_t step = walk.first; step < walk.hi; step += walk.stride, s_in += walk.stride) {
+    while (s_in >= p.steps_per_inst) s_in -= p.steps_per_inst, ++b;
+    const int64_t u = s_in * 32 + lane;
+    if (b != cur_b) {
+      if (cur_b >= 0) flush_instance<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c);
+      cur_b = b;
+    }
+    if (u >= p.units) continue;
+    const TT* __restrict__ pb = reinterpret_cast<const TT*>(p.logits) + (int64_t)b * p.V;  // `logits` carries pred
+    const TT* __restrict__ tb = p.target ? reinterpret_cast<const TT*>(p.target) + (int64_t)b * p.V : nullptr;
     int pr[VEC], t[VEC];
-    Label<TT>::template load<VEC>(pb + u * VEC, pr);
+    load_labels<TT, VEC>(pb + u * VEC, pr);
     if (tb) {
-      Label<TT>::template load<VEC>(tb + u * VEC, t);
+      load_labels<TT, VEC>(tb + u * VEC, t);
     } else {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) t[i] = -1;
@@ -134,15 +155,8 @@ __global__ void __launch_bounds__(kThreads) label_stats_kernel(const LossParams 
       }
     }
   }
-  double vals[CC * 4];
-#pragma unroll
-  for (int c = 0; c < CC; ++c) {
-    vals[c * 4 + DS_STAT_NLL] = 0.0;
-    vals[c * 4 + DS_STAT_LABEL] = (double)lab_c[c];
-    vals[c * 4 + DS_STAT_PRED] = (double)pred_c[c];
-    vals[c * 4 + DS_STAT_TP] = (double)tp_c[c];
-  }
-  publish_stats<CC>(p, b, chunk, vals, s_red, s_scratch);
+  flush_final<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c);
+  finish_launch(p, s_scratch);
 }
 
 }  // namespace
@@ -152,7 +166,7 @@ using namespace ds;
 
 extern "C" size_t ds_dp_loss_workspace_bytes(int64_t B_local, int64_t C) {
   if (B_local <= 0 || C <= 0) return 0;
-  return ticket_bytes(B_local) + sizeof(double) * (size_t)(kMaxLossCtas + B_local) * (size_t)C * kStatsPerClass;
+  return header_bytes() + sizeof(unsigned long long) * (size_t)B_local * (size_t)C * kStatsPerClass;
 }
 
 extern "C" int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const void* target, int target_dtype,
@@ -265,7 +279,6 @@ extern "C" int ds_label_stats(const void* pred, int pred_dtype, const void* targ
   if (pred_dtype != DS_I64 && pred_dtype != DS_U8) return fail(DS_ERR_DTYPE, "%s: pred must be DS_I64 or DS_U8", who);
   if (target && target_dtype != pred_dtype) return fail(DS_ERR_DTYPE, "%s: pred and target must share a dtype", who);
   if (B <= 0 || V <= 0 || C < 1 || C > DS_MAX_CLASSES) return fail(DS_ERR_SHAPE, "%s: bad B / C / V", who);
-  if (B > 0x7fffffffLL / kMaxLossCtas) return fail(DS_ERR_SHAPE, "%s: B too large", who);
   if (int rc = ds_device_check()) return rc;
   LossParams p{};
   p.logits = pred, p.target = target, p.inst_stats = inst_stats;
@@ -274,8 +287,8 @@ extern "C" int ds_label_stats(const void* pred, int pred_dtype, const void* targ
   const int W = pred_dtype == DS_I64 ? 4 : 8;
   const bool vec = (V % W == 0) && aligned16(pred) && aligned16(target) && !env_int("DS_FORCE_SCALAR", 0);
   p.units = vec ? V / W : V;
-  p.chunks = pick_chunks(B, p.units);
-  const dim3 grid((unsigned)(B * p.chunks));
+  if (int rc = setup_tiles(p, who, true)) return rc;
+  const dim3 grid((unsigned)p.grid);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (pred_dtype == DS_I64) {
     if (vec) label_stats_kernel<int64_t, 4><<<grid, kThreads, 0, s>>>(p);

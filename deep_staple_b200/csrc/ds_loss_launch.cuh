@@ -7,7 +7,7 @@ namespace ds {
 
 template <typename LT, typename TT, int C, int VEC>
 int launch_cfg(const LossParams& p, bool grad, bool stats, cudaStream_t stream) {
-  const dim3 grid((unsigned)(p.B_local * p.chunks));
+  const dim3 grid((unsigned)p.grid);
   const bool dice = stats && p.dice_target != nullptr;
   if (grad && stats) {
     if (dice) loss_kernel<LT, TT, C, VEC, true, true, true><<<grid, kThreads, 0, stream>>>(p);

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kThreads) multiclass_vote_kernel(const McParam
     const LT* __restrict__ pl = lab_t + u * VPT;
     for (int64_t n = 0; n < N; ++n, pl += V) {
       int lab[VPT];
-      Label<LT>::template load<VPT>(pl, lab);
+      load_labels<LT, VPT>(pl, lab);
       const float w = s_w[n];
 #pragma unroll
       for (int c = 0; c < KC; ++c)
