@@ -28,19 +28,24 @@ int setup_tiles(LossParams& p, const char* who, bool stats) {
   const int64_t need = (p.n_steps + kWarps - 1) / kWarps;
   if (grid > need) grid = need;
   p.grid = (int)(grid < 1 ? 1 : grid);
-  // groups: the largest divisor of the grid that does not exceed the number of instances, so every
-  // group is a whole number of CTAs and a warp meets at most ~2 instance boundaries.  Kernels
-  // without statistics have nothing to flush: one group, one front.
-  int want = stats ? (int)(p.B_local < p.grid ? p.B_local : p.grid) : 1;
-  want = env_int("DS_LOSS_GROUPS", want);
-  if (want < 1) want = 1;
-  if (want > p.grid) want = p.grid;
-  p.groups = 1;
-  for (int d = want; d >= 1; --d)
-    if (p.grid % d == 0) {
-      p.groups = d;
-      break;
+  // groups (kernels with statistics): one group per instance when the instances fit the grid -- the
+  // grid is trimmed to a multiple of B so that every group is a whole number of CTAs, ranges coincide
+  // with instances and no warp ever crosses an instance boundary.  More instances than CTAs: every
+  // CTA is its own group and walks a range of whole / partial instances (its warps flush at each
+  // boundary; at most two CTAs touch one instance, so those atomics do not contend).  Kernels without
+  // statistics have nothing to flush: one group, one front.
+  int groups = 1;
+  if (stats) {
+    if (p.B_local <= p.grid) {
+      groups = (int)p.B_local;
+      p.grid = p.grid / groups * groups;
+    } else {
+      groups = p.grid;
     }
+  }
+  const int forced = env_int("DS_LOSS_GROUPS", 0);  // tuning experiments only
+  if (forced > 0 && forced <= p.grid && p.grid % forced == 0) groups = forced;
+  p.groups = groups;
   int bits_v = 0;
   while (((int64_t)1 << bits_v) < p.V) ++bits_v;
   int e = 62 - bits_v - 10;

@@ -36,7 +36,12 @@
 namespace ds {
 
 constexpr int kStatsPerClass = DS_STATS;
-constexpr int kWsCounters = 4;       // workspace header: [0] finished CTAs, rest padding (16 bytes)
+// workspace header: two-level arrival tickets (same-address atomics serialise at the L2, so ~600 CTAs
+// do not all knock on one counter).  Level 1: kTickets1 counters, 128 B apart (CTA i arrives at
+// counter i % kTickets1); the last arriver of each goes on to level 2.
+constexpr int kTickets1 = 32;
+constexpr int kTicketStride = 32;                                  // words (128 B)
+constexpr int kWsCounters = (1 + kTickets1) * kTicketStride;       // [0] level 2, [32 * (1 + i)] level 1
 
 enum LossMode {
   kModeDP = 0,   // coefficient g * w_b / V from the data parameters (ds_dp_loss_fwd_bwd)
@@ -286,7 +291,22 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   __shared__ int s_last;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(p.counters, 1u) == gridDim.x - 1) ? 1 : 0;
+  if (threadIdx.x == 0) {
+    const unsigned n1 = gridDim.x < (unsigned)kTickets1 ? gridDim.x : (unsigned)kTickets1;
+    const unsigned i1 = blockIdx.x % n1;
+    const unsigned expect1 = gridDim.x / n1 + (i1 < gridDim.x % n1 ? 1u : 0u);
+    unsigned int* t1 = p.counters + (1 + i1) * kTicketStride;
+    int last = 0;
+    if (atomicAdd(t1, 1u) == expect1 - 1) {
+      *t1 = 0u;  // leave the workspace clean for the next launch
+      __threadfence();
+      if (atomicAdd(p.counters, 1u) == n1 - 1) {
+        *p.counters = 0u;
+        last = 1;
+      }
+    }
+    s_last = last;
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -298,7 +318,6 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
     const double d = ((i % kStatsPerClass) == DS_STAT_NLL) ? (double)v * inv_scale : (double)v;
     __stcg(p.inst_stats + p.b_offset * S + i, d);
   }
-  if (threadIdx.x < kWsCounters) p.counters[threadIdx.x] = 0u;
   __threadfence();
   __syncthreads();
   if (p.finalize) finalize_block(p, scratch);
