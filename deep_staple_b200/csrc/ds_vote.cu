@@ -10,19 +10,27 @@
 // and reproduces the summation ORDER of ATen's CPU sum(dim=0) (rows sequential inside blocks of
 // 16, each full block folded into the next accumulator level), so that for identical weights the
 // fp32 vote -- and therefore the thresholded label -- is bit-identical to the reference.
+#include <type_traits>
+
 #include "ds_common.cuh"
 
 namespace ds {
 namespace {
 
 constexpr int kWChunk = 4096;  // candidate weights staged in shared memory per pass
-constexpr int kBatch = 8;      // candidate planes whose loads are in flight together (divides 16)
+#ifndef DS_VOTE_BATCH
+#define DS_VOTE_BATCH 8
+#endif
+#ifndef DS_VOTE_U8_VPT
+#define DS_VOTE_U8_VPT 16
+#endif
+constexpr int kBatch = DS_VOTE_BATCH;  // candidate planes whose loads are in flight together (divides 16)
 
 template <typename LT, bool VECP>
 struct VoteIn;
 template <>
 struct VoteIn<int64_t, true> {
-  static constexpr bool kBinaryPath = false;  // 8 B per voxel-candidate: already HBM-bound, keep registers for loads
+  static constexpr bool kBinaryPath = true;  // also makes the label test wait for ALL loads of the batch
   static constexpr int VPT = 4;  // 2 x 16 B
   struct Raw {
     uint4 a, b;
@@ -61,29 +69,41 @@ struct VoteIn<int64_t, false> {
 template <>
 struct VoteIn<uint8_t, true> {
   static constexpr bool kBinaryPath = true;  // 1 B per voxel-candidate: instruction issue is the limit
-  static constexpr int VPT = 16;  // 1 x 16 B
+  static constexpr int VPT = DS_VOTE_U8_VPT;  // one 16 B (or 8 B) load
+  static constexpr int W = VPT / 4;
   struct Raw {
-    uint4 a;
+    uint32_t w[W];
   };
-  static __device__ __forceinline__ Raw load(const uint8_t* p) { return {ldg_stream16(p)}; }
+  static __device__ __forceinline__ Raw load(const uint8_t* p) {
+    Raw r;
+    if constexpr (VPT == 16) {
+      const uint4 v = ldg_stream16(p);
+      r.w[0] = v.x, r.w[1] = v.y, r.w[2] = v.z, r.w[3] = v.w;
+    } else {
+      const uint2 v = ldg_stream8(p);
+      r.w[0] = v.x, r.w[1] = v.y;
+    }
+    return r;
+  }
   static __device__ __forceinline__ void to_float(const Raw& r, float (&f)[VPT]) {
-    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < W; ++i) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) f[4 * i + j] = (float)((w[i] >> (8 * j)) & 0xffu);
+      for (int j = 0; j < 4; ++j) f[4 * i + j] = (float)((r.w[i] >> (8 * j)) & 0xffu);
     }
   }
   static __device__ __forceinline__ uint32_t nonbinary_bits(const Raw& r) {
-    return (r.a.x | r.a.y | r.a.z | r.a.w) & 0xfefefefeu;
+    uint32_t o = 0u;
+#pragma unroll
+    for (int i = 0; i < W; ++i) o |= r.w[i];
+    return o & 0xfefefefeu;
   }
   static __device__ __forceinline__ void add_binary(const Raw& r, float w, float (&acc)[VPT]) {
-    const uint32_t wd[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < W; ++i) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (wd[i] & (1u << (8 * j))) acc[4 * i + j] = __fadd_rn(acc[4 * i + j], w);
+        if (r.w[i] & (1u << (8 * j))) acc[4 * i + j] = __fadd_rn(acc[4 * i + j], w);
     }
   }
 };
@@ -120,6 +140,13 @@ __device__ __forceinline__ void store_labels(OT* p, const bool (&on)[VPT]) {
         w[i] = (on[4 * i] ? 1u : 0u) | (on[4 * i + 1] ? 0x100u : 0u) | (on[4 * i + 2] ? 0x10000u : 0u) |
                (on[4 * i + 3] ? 0x1000000u : 0u);
       stg_stream16(p, make_uint4(w[0], w[1], w[2], w[3]));
+    } else if constexpr (VPT == 8) {
+      uint32_t w[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        w[i] = (on[4 * i] ? 1u : 0u) | (on[4 * i + 1] ? 0x100u : 0u) | (on[4 * i + 2] ? 0x10000u : 0u) |
+               (on[4 * i + 3] ? 0x1000000u : 0u);
+      stg_stream8(p, make_uint2(w[0], w[1]));
     } else if constexpr (VPT == 4) {
       stg_stream4(p, (on[0] ? 1u : 0u) | (on[1] ? 0x100u : 0u) | (on[2] ? 0x10000u : 0u) | (on[3] ? 0x1000000u : 0u));
     } else {
@@ -236,12 +263,15 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
       }
       if (active) {
         const LT* __restrict__ pl = lab_t + n0 * V + u * VPT;
-        for (int nb = 0; nb < nn; nb += kBatch) {
-          typename In::Raw raw[kBatch];
+        // one batch of BN candidate planes: all loads first, then the votes.  BN is a compile-time
+        // constant (8 for the body, 4 / 2 / 1 for the tail of N), so nothing in here is guarded by
+        // a run-time predicate and the predicate registers stay free for the label tests.
+        auto batch = [&](auto bn_tag, int nb) {
+          constexpr int BN = decltype(bn_tag)::value;
+          typename In::Raw raw[BN];
 #pragma unroll
-          for (int j = 0; j < kBatch; ++j)
-            if (nb + j < nn) raw[j] = In::load(pl + (int64_t)j * V);
-          pl += (int64_t)kBatch * V;
+          for (int j = 0; j < BN; ++j) raw[j] = In::load(pl + (int64_t)j * V);
+          pl += (int64_t)BN * V;
           // {0,1} labels (the reference's data): float(label) * w is exactly w or +0, so the vote is a
           // predicated add -- two instructions per voxel-candidate instead of convert + mul + add.
           // Any other label value in this batch of planes sends the thread down the general path.
@@ -249,31 +279,31 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
           if constexpr (In::kBinaryPath) {
             nonbin = 0u;
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j)
-              if (nb + j < nn) nonbin |= In::nonbinary_bits(raw[j]);
+            for (int j = 0; j < BN; ++j) nonbin |= In::nonbinary_bits(raw[j]);
           }
           if (In::kBinaryPath && nonbin == 0u) {
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j)
-              if (nb + j < nn) In::add_binary(raw[j], s_w[nb + j], acc[0]);
+            for (int j = 0; j < BN; ++j) In::add_binary(raw[j], s_w[nb + j], acc[0]);
           } else {
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j) {
-              if (nb + j < nn) {
-                const float w = s_w[nb + j];
-                float f[VPT];
-                In::to_float(raw[j], f);
-                // product and sum rounded separately, like ATen's mul followed by sum (no FMA)
+            for (int j = 0; j < BN; ++j) {
+              const float w = s_w[nb + j];
+              float f[VPT];
+              In::to_float(raw[j], f);
+              // product and sum rounded separately, like ATen's mul followed by sum (no FMA)
 #pragma unroll
-                for (int i = 0; i < VPT; ++i) acc[0][i] = __fadd_rn(acc[0][i], __fmul_rn(f[i], w));
-              }
+              for (int i = 0; i < VPT; ++i) acc[0][i] = __fadd_rn(acc[0][i], __fmul_rn(f[i], w));
             }
           }
+        };
+        int nb = 0;
+        for (; nb + kBatch <= nn; nb += kBatch) {
+          batch(std::integral_constant<int, kBatch>{}, nb);
           // ATen cascade: after every full block of 16 rows fold level 0 into level 1, after
           // every 256 rows level 1 into level 2, after every 4096 rows level 2 into level 3
-          const int64_t done = n0 + nb + kBatch;  // rows consumed if this batch was full
+          const int64_t done = n0 + nb + kBatch;
           if constexpr (LEVELS > 1) {
-            if ((done & 15) == 0 && done <= N) {
+            if ((done & 15) == 0) {
 #pragma unroll
               for (int i = 0; i < VPT; ++i) acc[1][i] = __fadd_rn(acc[1][i], acc[0][i]), acc[0][i] = 0.f;
               if constexpr (LEVELS > 2) {
@@ -289,6 +319,14 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
             }
           }
         }
+        // tail of N (never completes a block of 16: kBatch divides 16)
+        if constexpr (kBatch > 4) {
+          if (nn - nb >= 4) batch(std::integral_constant<int, 4>{}, nb), nb += 4;
+        }
+        if constexpr (kBatch > 2) {
+          if (nn - nb >= 2) batch(std::integral_constant<int, 2>{}, nb), nb += 2;
+        }
+        if (nn - nb >= 1) batch(std::integral_constant<int, 1>{}, nb), nb += 1;
       }
     }
     if (active) {
@@ -323,7 +361,7 @@ int launch_vote(const VoteParams& p0, cudaStream_t stream) {
   p.units = p.V / VPT;
   // grid: T targets x chunks, about `waves` full waves of resident CTAs, at least one iteration each
   const int sms = sm_count();
-  const int per_sm = env_int("DS_VOTE_CTAS_PER_SM", 4), waves = env_int("DS_VOTE_WAVES", 4);
+  const int per_sm = env_int("DS_VOTE_CTAS_PER_SM", 4), waves = env_int("DS_VOTE_WAVES", 16);
   int64_t want = ((int64_t)sms * per_sm * waves + p.T - 1) / p.T;
   const int64_t max_chunks = (p.units + kThreads - 1) / kThreads;
   if (want > max_chunks) want = max_chunks;
