@@ -1,0 +1,79 @@
+"""Worker of tests/test_gpu_distributed.py (launched by torch.distributed.run, one rank per GPU, NCCL):
+the data-parallel loss and the target-sharded consensus must reproduce the single-GPU results."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+
+import deep_staple_b200 as ds  # noqa: E402
+from deep_staple_b200 import distributed as dd  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+
+    # ---- data-parallel loss (cfg5 shape class: 3 classes) -------------------------------------------
+    gen = torch.Generator().manual_seed(0)
+    B_local, C, shape, M = 2, 3, (16, 20, 24), 40
+    B = B_local * world
+    logits = (2 * torch.randn((B, C, *shape), generator=gen)).to(dev)
+    target = torch.randint(0, C, (B, *shape), generator=gen).to(dev)
+    emb_w = torch.randn((M, 1), generator=gen)
+    idx = torch.randperm(M, generator=gen)[:B].to(dev)
+    fixed = (torch.rand(M, generator=gen) * 3 + 1).to(dev)
+    cw = (torch.rand(C, generator=gen) + 0.5).to(dev)
+    sl = slice(rank * B_local, (rank + 1) * B_local)
+
+    emb = nn.Embedding(M, 1, sparse=True, _weight=emb_w.clone()).to(dev)
+    z = logits[sl].clone().requires_grad_(True)
+    out = dd.dp_weighted_loss_distributed(z, target[sl], emb, idx[sl], fixed, True, grad_scaler=128.0,
+                                          class_weights=cw, return_all=True)
+    (out.dp_loss * 128.0).backward()
+
+    emb1 = nn.Embedding(M, 1, sparse=True, _weight=emb_w.clone()).to(dev)
+    z1 = logits.clone().requires_grad_(True)
+    ref = ds.dp_weighted_loss(z1, target, (emb1, idx), fixed[idx], True, grad_scaler=128.0, class_weights=cw,
+                              return_all=True)
+    (ref.dp_loss * 128.0).backward()
+
+    def close(a, b, rtol, what):
+        err = float((a.double() - b.double()).abs().max())
+        scale = float(b.double().abs().max())
+        assert err <= rtol * scale + 1e-12, f"rank {rank} {what}: err {err:.3e} scale {scale:.3e}"
+
+    close(out.dp_loss, ref.dp_loss, 1e-6, "dp_loss")
+    assert torch.equal(out.inst_stats, ref.inst_stats), "statistics must be bit-identical (exact integer reduction)"
+    g, g1 = emb.weight.grad.coalesce(), emb1.weight.grad.coalesce()
+    assert g.is_sparse and torch.equal(g.indices(), g1.indices())  # ALL global rows on every rank
+    close(g.values(), g1.values(), 1e-6, "sparse data-parameter gradient")
+    close(z.grad, z1.grad[sl], 1e-6, "local logits gradient")
+    # the global label histogram (normaliser of the class-weighted CE under data parallelism)
+    counts = dd.global_class_counts(out.inst_stats[sl, :, 1].sum(0))
+    assert torch.equal(counts, torch.bincount(target.reshape(-1), minlength=C).double())
+
+    # ---- target-sharded consensus -------------------------------------------------------------------
+    T, N, S = 5, 10, (16, 16, 32)
+    gen = torch.Generator().manual_seed(1)
+    labels = (torch.rand((T, N, *S), generator=gen) < 0.4).to(torch.uint8).to(dev)
+    dps = torch.randn((T, N), generator=gen).to(dev)
+    lo, hi = dd.shard_range(T, rank, world)
+    full, ties = dd.sharded_consensus(labels[lo:hi], dps[lo:hi], T, gather=True, count_near_ties=True)
+    ref_c, ref_t = ds.consensus_batched(labels, dps, count_near_ties=True)
+    assert torch.equal(full, ref_c) and int(ties) == int(ref_t)
+    dist.barrier()
+    if rank == 0:
+        print("DIST_OK", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
