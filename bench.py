@@ -44,6 +44,10 @@ if ROOT not in sys.path:
 
 METRIC = "Gvoxel-candidates/s"
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused loss kernel on this workload,
+# from the `ncu --set full` capture summarised in profiles/r01_loss_fwdbwd_ncu_summary.txt
+# (268.5 MB read + 96.5 MB written; the rest of the 134 MB of gradients is still dirty in L2 at kernel end)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 365_070_848
 
 LOSS_CFG = dict(B=8, C=2, S=(128, 128, 128), M=600, grad_scale=65536.0)
 VOTE_CFG = dict(T_global=100, N=30, S=(128, 128, 128))
@@ -488,7 +492,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": loss_config_dict(world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "ds::loss_kernel<float,int64,2,4,true,true>",
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_loss_fwdbwd_ncu_summary.txt",
+                         "kernel": "ds::loss_kernel<float,int64,2,4,true,true>",
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": ksec / args.steps * 1e6,
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "vote": vote,
