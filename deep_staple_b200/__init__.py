@@ -23,5 +23,6 @@ from .loss import (  # noqa: F401
 )
 from .metrics import dice_from_label_maps, dice_from_stats, prepass_constants  # noqa: F401
 from .snapshot import build_snapshot, load_snapshot, save_snapshot  # noqa: F401
+from . import distributed  # noqa: F401,E402
 
 __version__ = "0.1.0"
