@@ -213,17 +213,17 @@ def run_reference_arm(args):
         "note": "reference = torch CPU path of main_deep_staple.py:716,738-762 (oracle port; the reference code is "
                 "inline in train_DL and cannot be imported), all host threads",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
-def loss_config_dict(n_gpus):
+def loss_config_dict(n_gpus, exchange="inside the loss kernel over NVLink peer memory"):
     c = LOSS_CFG
     return {
         "workload": "dp-weighted CE loss fwd+bwd (risk regularisation, fixed weighting, class-weighted CE value, "
                     "hard-Dice statistics), batch 8 x 2 classes x 128^3 per GPU (BASELINE.json configs[1])",
         "batch_per_gpu": c["B"], "global_batch": c["B"] * n_gpus, "classes": c["C"], "volume": list(c["S"]),
         "logits_dtype": "float32", "label_dtype": "int64", "grad_scale": c["grad_scale"],
-        "parallelism": f"dp{n_gpus} (instances sharded; all-gather of per-instance statistics)" if n_gpus > 1 else "single GPU",
+        "parallelism": f"dp{n_gpus} (instances sharded; per-instance statistics exchanged {exchange})" if n_gpus > 1 else "single GPU",
         "l2": "inputs rotate over 3 buffer sets of 403 MB (> 126 MB L2); no reuse between steps",
     }
 
@@ -234,7 +234,7 @@ def loss_config_dict(n_gpus):
 class LossStep:
     """Preallocated buffers + the raw C-ABI call of one step (what `value` and `roofline` time)."""
 
-    def __init__(self, device, n_sets, rank, world):
+    def __init__(self, device, n_sets, rank, world, exchange="fused"):
         import deep_staple_b200 as ds
         from deep_staple_b200 import _binding as b
 
@@ -261,6 +261,11 @@ class LossStep:
         self.ws = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
         self.stream = torch.cuda.current_stream(device).cuda_stream
         self.i = 0
+        self.exchange = None
+        if world > 1 and exchange == "fused":
+            from deep_staple_b200.distributed import FusedExchange
+
+            self.exchange = FusedExchange.get(self.B_total, self.C, device)
 
     def kernel(self):
         b, k = self.b, self.i % len(self.sets)
@@ -274,7 +279,24 @@ class LossStep:
         if rc:
             b.check(rc, "ds_dp_loss_fwd_bwd")
 
+    def fused_step(self):
+        """data-parallel step as ONE launch: statistics exchange over NVLink peer memory + epilogue in the kernel tail"""
+        b, k, ex = self.b, self.i % len(self.sets), self.exchange
+        self.i += 1
+        s = self.sets[k]
+        rc = self.lib.ds_dp_loss_fwd_bwd_exchange(
+            s["logits"].data_ptr(), b.DS_F32, s["target"].data_ptr(), b.DS_I64, None, self.B, self.C, self.V,
+            self.bare.data_ptr(), self.fixed.data_ptr(), self.B_total, self.rank * self.B, self.cw.data_ptr(), 1,
+            self.scale.data_ptr(), self.dlogits[k].data_ptr(), self.stats.data_ptr(), self.loss_out.data_ptr(),
+            self.d_bare.data_ptr(), self.per_inst.data_ptr(), ex.peer_bases.data_ptr(), ex.rank, ex.world,
+            ex.next_epoch(), self.ws.data_ptr(), self.ws.numel() * 8, self.stream)
+        if rc:
+            b.check(rc, "ds_dp_loss_fwd_bwd_exchange")
+
     def step(self):
+        if self.exchange is not None:
+            self.fused_step()
+            return
         self.kernel()
         if self.world > 1:
             import torch.distributed as dist
@@ -401,7 +423,27 @@ def vote_section(device, rank, world, steps, warmup, peak):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything but the final JSON line goes to stderr: libraries (NCCL's version banner, c10d) write to
+    file descriptor 1 directly, and the contract is ONE JSON line on stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -411,6 +453,8 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-vote", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: statistics exchange inside the loss kernel over NVLink peer memory, or NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -435,7 +479,7 @@ def main():
     import deep_staple_b200 as ds
 
     peak, peak_src = peak_hbm()
-    step = LossStep(device, 3, rank, world)
+    step = LossStep(device, 3, rank, world, args.exchange)
     c = LOSS_CFG
     vox_per_step = step.B * step.V  # voxel-instances per GPU per step
 
@@ -446,6 +490,8 @@ def main():
     launches0 = ds.launch_count()
     sec = timed(step.step, args.steps, 0, barrier)
     launches = ds.launch_count() - launches0
+    if dist:
+        dist.barrier()  # nobody leaves the fused-exchange phase while a peer still waits on its flags
     if dist:
         tmax = torch.tensor([sec], device=device, dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -490,7 +536,8 @@ def main():
             "metric": METRIC, "value": world * vox_per_step * args.steps / sec / 1e9, "unit": "Gvoxel-candidates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": loss_config_dict(world),
+            "config": loss_config_dict(world, "inside the loss kernel over NVLink peer memory" if args.exchange == "fused"
+                                       else "by NCCL all-gather + epilogue launch"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_loss_fwdbwd_ncu_summary.txt",
                          "kernel": "ds::loss_kernel<float,int64,2,4,true,true>",
@@ -498,7 +545,7 @@ def main():
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "vote": vote,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()

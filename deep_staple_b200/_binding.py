@@ -41,6 +41,11 @@ SIGNATURES = {
     "ds_dp_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                    c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ds_dp_loss_exchange_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "ds_dp_loss_fwd_bwd_exchange": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64,
+                                            c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_uint64,
+                                            c_void_p, c_size_t, c_void_p]),
     "ds_dp_loss_finalize": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ds_weighted_ce_fwd_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p,

@@ -174,29 +174,68 @@ extern "C" size_t ds_dp_loss_workspace_bytes(int64_t B_local, int64_t C) {
   return header_bytes() + sizeof(unsigned long long) * (size_t)B_local * (size_t)C * kStatsPerClass;
 }
 
+namespace {
+int dp_loss_fwd_bwd_impl(const char* who, const void* logits, int logit_dtype, const void* target, int target_dtype,
+                         const void* dice_target, int64_t B_local, int64_t C, int64_t V, const float* bare_weight,
+                         const float* fixed_w, int64_t B_total, int64_t b_offset, const float* class_w, int use_risk,
+                         const float* grad_scale, void* dlogits, double* inst_stats, float* loss_out,
+                         float* d_bare_weight, float* per_inst_out, const unsigned long long* peer_bases, int rank,
+                         int world, unsigned long long epoch, void* workspace, size_t workspace_bytes,
+                         ds_stream_t stream) {
+  if (int rc = check_common(who, logits, logit_dtype, target, target_dtype, B_local, C, V)) return rc;
+  if (!bare_weight) return fail(DS_ERR_NULL, "%s: bare_weight is required", who);
+  if (!peer_bases && !inst_stats) return fail(DS_ERR_NULL, "%s: inst_stats is required", who);
+  if (B_total < B_local || b_offset < 0 || b_offset + B_local > B_total)
+    return fail(DS_ERR_ARG, "%s: rows [%lld, %lld) do not fit a batch of %lld", who, (long long)b_offset,
+                (long long)(b_offset + B_local), (long long)B_total);
+  if (B_total > DS_MAX_BATCH) return fail(DS_ERR_SHAPE, "%s: B_total=%lld exceeds %d", who, (long long)B_total, DS_MAX_BATCH);
+  const bool whole = B_local == B_total;
+  if ((whole || peer_bases) && !loss_out) return fail(DS_ERR_NULL, "%s: loss_out is required", who);
+  if (peer_bases && (world < 1 || world > kThreads || rank < 0 || rank >= world || epoch == 0))
+    return fail(DS_ERR_ARG, "%s: bad rank/world/epoch %d/%d/%llu", who, rank, world, epoch);
+  LossParams p{};
+  p.logits = logits, p.target = target, p.dice_target = dice_target, p.dlogits = dlogits;
+  p.bare_weight = bare_weight, p.fixed_w = fixed_w, p.class_w = class_w, p.grad_scale = grad_scale;
+  p.inst_stats = inst_stats, p.loss_out = loss_out, p.d_bare_weight = d_bare_weight, p.per_inst_out = per_inst_out;
+  p.B_local = B_local, p.B_total = B_total, p.b_offset = b_offset, p.V = V, p.C = (int)C;
+  p.use_risk = use_risk ? 1 : 0, p.mode = kModeDP, p.finalize = (whole || peer_bases) ? 1 : 0, p.dp_outputs = 1;
+  p.peer_bases = peer_bases, p.rank = rank, p.world = world, p.epoch = epoch;
+  if (int rc = carve_workspace(p, workspace, workspace_bytes, who)) return rc;
+  return launch_loss(p, logit_dtype, target_dtype, dlogits != nullptr, true, reinterpret_cast<cudaStream_t>(stream));
+}
+}  // namespace
+
 extern "C" int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const void* target, int target_dtype,
                                   const void* dice_target, int64_t B_local, int64_t C, int64_t V,
                                   const float* bare_weight, const float* fixed_w, int64_t B_total, int64_t b_offset,
                                   const float* class_w, int use_risk, const float* grad_scale, void* dlogits,
                                   double* inst_stats, float* loss_out, float* d_bare_weight, float* per_inst_out,
                                   void* workspace, size_t workspace_bytes, ds_stream_t stream) {
-  const char* who = "ds_dp_loss_fwd_bwd";
-  if (int rc = check_common(who, logits, logit_dtype, target, target_dtype, B_local, C, V)) return rc;
-  if (!bare_weight || !inst_stats) return fail(DS_ERR_NULL, "%s: bare_weight and inst_stats are required", who);
-  if (B_total < B_local || b_offset < 0 || b_offset + B_local > B_total)
-    return fail(DS_ERR_ARG, "%s: rows [%lld, %lld) do not fit a batch of %lld", who, (long long)b_offset,
-                (long long)(b_offset + B_local), (long long)B_total);
-  if (B_total > DS_MAX_BATCH) return fail(DS_ERR_SHAPE, "%s: B_total=%lld exceeds %d", who, (long long)B_total, DS_MAX_BATCH);
-  const bool whole = B_local == B_total;
-  if (whole && !loss_out) return fail(DS_ERR_NULL, "%s: loss_out is required when the batch is local", who);
-  LossParams p{};
-  p.logits = logits, p.target = target, p.dice_target = dice_target, p.dlogits = dlogits;
-  p.bare_weight = bare_weight, p.fixed_w = fixed_w, p.class_w = class_w, p.grad_scale = grad_scale;
-  p.inst_stats = inst_stats, p.loss_out = loss_out, p.d_bare_weight = d_bare_weight, p.per_inst_out = per_inst_out;
-  p.B_local = B_local, p.B_total = B_total, p.b_offset = b_offset, p.V = V, p.C = (int)C;
-  p.use_risk = use_risk ? 1 : 0, p.mode = kModeDP, p.finalize = whole ? 1 : 0, p.dp_outputs = 1;
-  if (int rc = carve_workspace(p, workspace, workspace_bytes, who)) return rc;
-  return launch_loss(p, logit_dtype, target_dtype, dlogits != nullptr, true, reinterpret_cast<cudaStream_t>(stream));
+  return dp_loss_fwd_bwd_impl("ds_dp_loss_fwd_bwd", logits, logit_dtype, target, target_dtype, dice_target, B_local, C,
+                              V, bare_weight, fixed_w, B_total, b_offset, class_w, use_risk, grad_scale, dlogits,
+                              inst_stats, loss_out, d_bare_weight, per_inst_out, nullptr, 0, 1, 0, workspace,
+                              workspace_bytes, stream);
+}
+
+extern "C" size_t ds_dp_loss_exchange_bytes(int64_t B_total, int64_t C, int world) {
+  if (B_total <= 0 || C <= 0 || world <= 0) return 0;
+  return sizeof(double) * 2 * (size_t)B_total * (size_t)C * kStatsPerClass + sizeof(unsigned long long) * (size_t)world;
+}
+
+extern "C" int ds_dp_loss_fwd_bwd_exchange(const void* logits, int logit_dtype, const void* target, int target_dtype,
+                                           const void* dice_target, int64_t B_local, int64_t C, int64_t V,
+                                           const float* bare_weight, const float* fixed_w, int64_t B_total,
+                                           int64_t b_offset, const float* class_w, int use_risk,
+                                           const float* grad_scale, void* dlogits, double* inst_stats,
+                                           float* loss_out, float* d_bare_weight, float* per_inst_out,
+                                           const unsigned long long* peer_bases, int rank, int world,
+                                           unsigned long long epoch, void* workspace, size_t workspace_bytes,
+                                           ds_stream_t stream) {
+  if (!peer_bases) return fail(DS_ERR_NULL, "ds_dp_loss_fwd_bwd_exchange: peer_bases is required");
+  return dp_loss_fwd_bwd_impl("ds_dp_loss_fwd_bwd_exchange", logits, logit_dtype, target, target_dtype, dice_target,
+                              B_local, C, V, bare_weight, fixed_w, B_total, b_offset, class_w, use_risk, grad_scale,
+                              dlogits, inst_stats, loss_out, d_bare_weight, per_inst_out, peer_bases, rank, world, epoch,
+                              workspace, workspace_bytes, stream);
 }
 
 extern "C" int ds_dp_loss_finalize(const double* inst_stats, int64_t B_total, int64_t C, int64_t V,

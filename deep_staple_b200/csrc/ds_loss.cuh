@@ -72,6 +72,10 @@ struct LossParams {
   int64_t weight_stride;        // kModeBwd: stride of inst_weight
   double nll_scale;             // fixed-point scale of the loss sums (power of two)
   int C, use_risk, mode, finalize, dp_outputs, grid, groups;
+  // fused multi-GPU exchange (ds_dp_loss_fwd_bwd_exchange): peer-mapped exchange buffers, see finish_launch
+  const unsigned long long* peer_bases;  // device array [world]: base address of every rank's exchange buffer
+  unsigned long long epoch;              // step counter, identical on all ranks, starts at 1
+  int rank, world;
 };
 
 // sigmoid of a data parameter (:743): fp32 like the reference, widened for the batch sums
@@ -312,15 +316,70 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   __threadfence();
   const int S = p.C * kStatsPerClass;
   const double inv_scale = 1.0 / p.nll_scale;
+  if (p.peer_bases == nullptr) {
+    for (int64_t i = threadIdx.x; i < p.B_local * S; i += kThreads) {
+      const long long v = (long long)__ldcg(p.acc + i);
+      __stcg(p.acc + i, 0ull);
+      const double d = ((i % kStatsPerClass) == DS_STAT_NLL) ? (double)v * inv_scale : (double)v;
+      __stcg(p.inst_stats + p.b_offset * S + i, d);
+    }
+    __threadfence();
+    __syncthreads();
+    if (p.finalize) finalize_block(p, scratch);
+    return;
+  }
+  // ---- fused exchange over NVLink peer memory (data-parallel loss) --------------------------------
+  // Every rank owns an exchange buffer mapped into all peers:
+  //   [2][B_total * S] doubles (statistics, double-buffered by step parity) | [world] u64 arrival flags.
+  // This CTA stores the rank's rows straight into EVERY rank's buffer, publishes "rows of step `epoch`
+  // have landed" in each peer's flag word, waits until all peers did the same here, and then runs the
+  // batch epilogue on the complete statistics -- no separate all-gather, no second launch.
+  // A peer can be at most one step ahead (it needs our flag of step k+1 to finish step k+1), so two
+  // statistic slots are enough.
+  const int64_t n_all = p.B_total * S;
+  auto slot_of = [&](unsigned long long base) -> double* {
+    return reinterpret_cast<double*>(base) + (p.epoch & 1ull) * n_all;
+  };
+  auto flags_of = [&](unsigned long long base) -> unsigned long long* {
+    return reinterpret_cast<unsigned long long*>(base) + 2 * n_all;
+  };
   for (int64_t i = threadIdx.x; i < p.B_local * S; i += kThreads) {
     const long long v = (long long)__ldcg(p.acc + i);
     __stcg(p.acc + i, 0ull);
     const double d = ((i % kStatsPerClass) == DS_STAT_NLL) ? (double)v * inv_scale : (double)v;
-    __stcg(p.inst_stats + p.b_offset * S + i, d);
+    for (int q = 0; q < p.world; ++q) slot_of(__ldg(p.peer_bases + q))[p.b_offset * S + i] = d;
   }
-  __threadfence();
+  __threadfence_system();
   __syncthreads();
-  if (p.finalize) finalize_block(p, scratch);
+  __shared__ int s_timeout;
+  if (threadIdx.x == 0) s_timeout = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < p.world) {
+    const int q = threadIdx.x;
+    unsigned long long* theirs = flags_of(__ldg(p.peer_bases + q)) + p.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(p.epoch) : "memory");
+    const unsigned long long* mine = flags_of(__ldg(p.peer_bases + p.rank)) + q;
+    unsigned long long seen = 0ull, t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+      if (seen >= p.epoch) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived -- give up instead of hanging the GPU
+        s_timeout = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  __threadfence();
+  LossParams full = p;
+  full.inst_stats = slot_of(__ldg(p.peer_bases + p.rank));
+  if (p.inst_stats)
+    for (int64_t i = threadIdx.x; i < n_all; i += kThreads) p.inst_stats[i] = __ldcg(full.inst_stats + i);
+  finalize_block(full, scratch);
+  if (s_timeout && threadIdx.x == 0 && p.loss_out) p.loss_out[0] = p.loss_out[1] = __int_as_float(0x7fc00000);
 }
 
 // Static schedule of one warp (see the header comment): steps first, first + stride, ... < hi.

@@ -29,6 +29,7 @@ import torch.distributed as dist
 from . import _binding as _b
 
 __all__ = [
+    "FusedExchange",
     "shard_range",
     "gather_batch_indices",
     "exchange_instance_stats",
@@ -36,6 +37,46 @@ __all__ = [
     "dp_weighted_loss_distributed",
     "global_class_counts",
 ]
+
+
+class FusedExchange:
+    """Peer-mapped exchange buffers for ``ds_dp_loss_fwd_bwd_exchange``: the statistics exchange of the
+    data-parallel loss happens INSIDE the loss kernel (stores into every rank's buffer over NVLink /
+    NVSwitch peer memory + arrival flags), replacing the NCCL all-gather and the separate epilogue launch.
+
+    One symmetric allocation per (group, B_global, C), made with ``torch.distributed._symmetric_memory``
+    (CUDA VMM / fabric handles exchanged through the process group's store).  All ranks must construct
+    it collectively and then make the same sequence of loss calls (the step counter ``epoch`` must agree)."""
+
+    _cache = {}
+
+    def __init__(self, b_total: int, num_classes: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        lib = _b.load()
+        nbytes = int(lib.ds_dp_loss_exchange_bytes(b_total, num_classes, self.world))
+        self.buf = symm_mem.empty((nbytes + 7) // 8, dtype=torch.int64, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        ptrs = [int(x) for x in self.handle.buffer_ptrs]
+        offset = self.buf.data_ptr() - ptrs[self.rank]  # the tensor may sit inside a larger symmetric block
+        self.peer_bases = torch.tensor([x + offset for x in ptrs], dtype=torch.int64, device=device)
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every buffer is zeroed before anyone's first flag can arrive
+
+    @classmethod
+    def get(cls, b_total: int, num_classes: int, device: torch.device, group=None) -> "FusedExchange":
+        key = (id(group), b_total, num_classes, device.index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(b_total, num_classes, device, group)
+        return cls._cache[key]
+
+    def next_epoch(self) -> int:
+        self.epoch += 1
+        return self.epoch
 
 
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -128,7 +169,7 @@ class _DistributedDPLoss(torch.autograd.Function):
     """Fused local pass + statistics exchange + replicated epilogue (see module docstring)."""
 
     @staticmethod
-    def forward(ctx, dp_logits, bare_global, target, fixed_global, use_risk, scale, class_w, b_offset, group):
+    def forward(ctx, dp_logits, bare_global, target, fixed_global, use_risk, scale, class_w, b_offset, group, fused):
         from .loss import _flat_inputs, _workspace
 
         z, t, B_local, C, V = _flat_inputs(dp_logits, target)
@@ -146,20 +187,32 @@ class _DistributedDPLoss(torch.autograd.Function):
         lib = _b.load()
         with torch.cuda.device(dev):
             ws = _workspace(dev, B_local, C)
-            rc = lib.ds_dp_loss_fwd_bwd(
-                _b.ptr(z), _b.logit_dtype(z), _b.ptr(t), _b.label_dtype(t), None, B_local, C, V, _b.ptr(bare),
-                _b.ptr(fixed), B_total, b_offset, _b.ptr(cw), 1 if use_risk else 0, _b.ptr(scale), _b.ptr(dlogits),
-                _b.ptr(stats), _b.ptr(loss_out), _b.ptr(d_bare), _b.ptr(per_inst), _b.ptr(ws), ws.numel() * 8,
-                _b.stream_ptr(dev),
-            )
-            _b.check(rc, "ds_dp_loss_fwd_bwd")
-            if B_local != B_total:
-                exchange_instance_stats(stats, b_offset, B_local, group)
-                rc = lib.ds_dp_loss_finalize(
-                    _b.ptr(stats), B_total, C, V, _b.ptr(bare), _b.ptr(fixed), _b.ptr(cw), 1 if use_risk else 0,
-                    _b.ptr(scale), _b.ptr(loss_out), _b.ptr(d_bare), _b.ptr(per_inst), _b.stream_ptr(dev),
+            if fused and B_local != B_total:
+                # statistics exchange + epilogue inside the loss kernel (peer memory over NVLink)
+                ex = FusedExchange.get(B_total, C, dev, group)
+                rc = lib.ds_dp_loss_fwd_bwd_exchange(
+                    _b.ptr(z), _b.logit_dtype(z), _b.ptr(t), _b.label_dtype(t), None, B_local, C, V, _b.ptr(bare),
+                    _b.ptr(fixed), B_total, b_offset, _b.ptr(cw), 1 if use_risk else 0, _b.ptr(scale),
+                    _b.ptr(dlogits), _b.ptr(stats), _b.ptr(loss_out), _b.ptr(d_bare), _b.ptr(per_inst),
+                    _b.ptr(ex.peer_bases), ex.rank, ex.world, ex.next_epoch(), _b.ptr(ws), ws.numel() * 8,
+                    _b.stream_ptr(dev),
                 )
-                _b.check(rc, "ds_dp_loss_finalize")
+                _b.check(rc, "ds_dp_loss_fwd_bwd_exchange")
+            else:
+                rc = lib.ds_dp_loss_fwd_bwd(
+                    _b.ptr(z), _b.logit_dtype(z), _b.ptr(t), _b.label_dtype(t), None, B_local, C, V, _b.ptr(bare),
+                    _b.ptr(fixed), B_total, b_offset, _b.ptr(cw), 1 if use_risk else 0, _b.ptr(scale),
+                    _b.ptr(dlogits), _b.ptr(stats), _b.ptr(loss_out), _b.ptr(d_bare), _b.ptr(per_inst), _b.ptr(ws),
+                    ws.numel() * 8, _b.stream_ptr(dev),
+                )
+                _b.check(rc, "ds_dp_loss_fwd_bwd")
+                if B_local != B_total:
+                    exchange_instance_stats(stats, b_offset, B_local, group)
+                    rc = lib.ds_dp_loss_finalize(
+                        _b.ptr(stats), B_total, C, V, _b.ptr(bare), _b.ptr(fixed), _b.ptr(cw), 1 if use_risk else 0,
+                        _b.ptr(scale), _b.ptr(loss_out), _b.ptr(d_bare), _b.ptr(per_inst), _b.stream_ptr(dev),
+                    )
+                    _b.check(rc, "ds_dp_loss_finalize")
         ctx.assumed = scale
         ctx.bare_shape = bare_global.shape
         ctx.logits_shape = dp_logits.shape
@@ -183,7 +236,7 @@ class _DistributedDPLoss(torch.autograd.Function):
                                             _b.ptr(one), _b.stream_ptr(dlogits.device))
             _b.check(rc, "ds_rescale_inplace")
             grad_logits = dlogits.view(ctx.logits_shape)
-        return grad_logits, grad_bare, None, None, None, None, None, None, None
+        return grad_logits, grad_bare, None, None, None, None, None, None, None, None
 
 
 def dp_weighted_loss_distributed(
@@ -198,12 +251,17 @@ def dp_weighted_loss_distributed(
     class_weights: Optional[torch.Tensor] = None,
     group=None,
     return_all: bool = False,
+    exchange: str = "fused",
 ):
     """Data-parallel form of ``dp_weighted_loss``: each rank passes ITS instances (``dp_logits``,
     ``b_seg_modified``, ``b_idxs_dataset``), the replicated ``embedding`` and the FULL
     ``fixed_weighting`` table (:653).  Returns the loss of the GLOBAL batch (identical on every rank);
     ``backward`` delivers sparse gradient rows for all ``B_global`` data parameters on every rank (so
-    the replicas stay identical) and, if ``dp_logits`` requires grad, this rank's logits gradient."""
+    the replicas stay identical) and, if ``dp_logits`` requires grad, this rank's logits gradient.
+    ``exchange``: ``"fused"`` -- the statistics travel inside the loss kernel over NVLink peer memory
+    (``FusedExchange``); ``"nccl"`` -- fused kernel + NCCL all-gather + epilogue kernel."""
+    if exchange not in ("fused", "nccl"):
+        raise ValueError("exchange must be 'fused' or 'nccl'")
     from .loss import DPLossOutput, _scale_tensor
 
     idx_global, b_offset = gather_batch_indices(b_idxs_dataset.to(dp_logits.device), group)
@@ -212,7 +270,7 @@ def dp_weighted_loss_distributed(
     scale = _scale_tensor(grad_scaler, dp_logits.device)
     loss, ce, per_inst, stats = _DistributedDPLoss.apply(
         dp_logits, bare_global, b_seg_modified, fixed_global, bool(use_risk_regularization), scale, class_weights,
-        b_offset, group,
+        b_offset, group, exchange == "fused",
     )
     if not return_all:
         return loss

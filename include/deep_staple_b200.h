@@ -153,7 +153,8 @@ int ds_consensus_vote_sparse(const int64_t* voxel_index, const int64_t* values, 
  * d_bare_weight [B_total] floats: g * dL/dp_b            > written only when B_local == B_total
  * per_inst_out  [B_total, DS_INST] floats               /
  * workspace     ds_dp_loss_workspace_bytes(B_local, C) bytes, 16-byte aligned, ZERO-FILLED once by
- *               the caller before first use (the kernel leaves its ticket counters zero again).
+ *               the caller before first use (arrival tickets + exact 64-bit integer accumulators;
+ *               every launch leaves it all-zero again).
  * ------------------------------------------------------------------------------------------- */
 size_t ds_dp_loss_workspace_bytes(int64_t B_local, int64_t C);
 
@@ -163,6 +164,28 @@ int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const void* target, 
                        const float* class_w, int use_risk, const float* grad_scale, void* dlogits,
                        double* inst_stats, float* loss_out, float* d_bare_weight, float* per_inst_out,
                        void* workspace, size_t workspace_bytes, ds_stream_t stream);
+
+/* Data-parallel form with the statistics exchange FUSED into the kernel tail (no NCCL call, no
+ * second launch): every rank owns an exchange buffer of ds_dp_loss_exchange_bytes(B_total, C, world)
+ * bytes (zero-filled once) that is mapped into all peers (NVLink / NVSwitch peer memory, e.g. a
+ * torch.distributed._symmetric_memory allocation); `peer_bases` is a DEVICE array [world] with the
+ * address of every rank's buffer as seen from this GPU.  The last CTA stores this rank's rows of the
+ * statistics into every rank's buffer, raises its arrival flag there, waits for all peers' flags here
+ * and runs the batch epilogue on the complete [B_total, C, DS_STATS] statistics, so loss_out,
+ * d_bare_weight, per_inst_out (and inst_stats, if not NULL) are those of the GLOBAL batch on every
+ * rank.  `epoch` is a step counter that is identical on all ranks and starts at 1; all ranks must make
+ * the same sequence of calls.  A peer that does not arrive within 10 s yields NaN losses instead of
+ * a hang. */
+size_t ds_dp_loss_exchange_bytes(int64_t B_total, int64_t C, int world);
+
+int ds_dp_loss_fwd_bwd_exchange(const void* logits, int logit_dtype, const void* target, int target_dtype,
+                                const void* dice_target, int64_t B_local, int64_t C, int64_t V,
+                                const float* bare_weight, const float* fixed_w, int64_t B_total, int64_t b_offset,
+                                const float* class_w, int use_risk, const float* grad_scale, void* dlogits,
+                                double* inst_stats, float* loss_out, float* d_bare_weight, float* per_inst_out,
+                                const unsigned long long* peer_bases, int rank, int world,
+                                unsigned long long epoch, void* workspace, size_t workspace_bytes,
+                                ds_stream_t stream);
 
 /* Batch epilogue on already reduced statistics (multi-GPU: after the all-gather of inst_stats).
  *   s = sigmoid(p); m = mean(s); w = s / (m f)                      main_deep_staple.py:743-748

@@ -33,12 +33,6 @@ def main():
     cw = (torch.rand(C, generator=gen) + 0.5).to(dev)
     sl = slice(rank * B_local, (rank + 1) * B_local)
 
-    emb = nn.Embedding(M, 1, sparse=True, _weight=emb_w.clone()).to(dev)
-    z = logits[sl].clone().requires_grad_(True)
-    out = dd.dp_weighted_loss_distributed(z, target[sl], emb, idx[sl], fixed, True, grad_scaler=128.0,
-                                          class_weights=cw, return_all=True)
-    (out.dp_loss * 128.0).backward()
-
     emb1 = nn.Embedding(M, 1, sparse=True, _weight=emb_w.clone()).to(dev)
     z1 = logits.clone().requires_grad_(True)
     ref = ds.dp_weighted_loss(z1, target, (emb1, idx), fixed[idx], True, grad_scaler=128.0, class_weights=cw,
@@ -50,12 +44,23 @@ def main():
         scale = float(b.double().abs().max())
         assert err <= rtol * scale + 1e-12, f"rank {rank} {what}: err {err:.3e} scale {scale:.3e}"
 
-    close(out.dp_loss, ref.dp_loss, 1e-6, "dp_loss")
-    assert torch.equal(out.inst_stats, ref.inst_stats), "statistics must be bit-identical (exact integer reduction)"
-    g, g1 = emb.weight.grad.coalesce(), emb1.weight.grad.coalesce()
-    assert g.is_sparse and torch.equal(g.indices(), g1.indices())  # ALL global rows on every rank
-    close(g.values(), g1.values(), 1e-6, "sparse data-parameter gradient")
-    close(z.grad, z1.grad[sl], 1e-6, "local logits gradient")
+    # "fused": statistics exchange inside the loss kernel over NVLink peer memory (several steps, so the
+    # double-buffered slots and the epoch flags are exercised); "nccl": all-gather + epilogue launch
+    for exchange, repeats in (("fused", 5), ("nccl", 1)):
+        for it in range(repeats):
+            emb = nn.Embedding(M, 1, sparse=True, _weight=emb_w.clone()).to(dev)
+            z = logits[sl].clone().requires_grad_(True)
+            out = dd.dp_weighted_loss_distributed(z, target[sl], emb, idx[sl], fixed, True, grad_scaler=128.0,
+                                                  class_weights=cw, return_all=True, exchange=exchange)
+            (out.dp_loss * 128.0).backward()
+            what = f"{exchange}#{it}"
+            close(out.dp_loss, ref.dp_loss, 1e-6, what + " dp_loss")
+            close(out.ce_loss, ref.ce_loss, 1e-6, what + " ce_loss")
+            assert torch.equal(out.inst_stats, ref.inst_stats), what + ": statistics must be bit-identical (exact integer reduction)"
+            g, g1 = emb.weight.grad.coalesce(), emb1.weight.grad.coalesce()
+            assert g.is_sparse and torch.equal(g.indices(), g1.indices())  # ALL global rows on every rank
+            close(g.values(), g1.values(), 1e-6, what + " sparse data-parameter gradient")
+            close(z.grad, z1.grad[sl], 1e-6, what + " local logits gradient")
     # the global label histogram (normaliser of the class-weighted CE under data parallelism)
     counts = dd.global_class_counts(out.inst_stats[sl, :, 1].sum(0))
     assert torch.equal(counts, torch.bincount(target.reshape(-1), minlength=C).double())
