@@ -1,6 +1,7 @@
 // C-ABI entry points of the loss path: argument validation, launch geometry, the stand-alone
 // batch epilogue, the rescale helper and the label-statistics kernel.
 #include "ds_loss.cuh"
+#include "ds_loss_tma.cuh"
 
 namespace ds {
 
@@ -23,7 +24,8 @@ int setup_tiles(LossParams& p, const char* who, bool stats) {
   (void)who;
   p.steps_per_inst = (p.units + 31) / 32;
   p.n_steps = p.steps_per_inst * p.B_local;
-  const int per_sm = env_int("DS_LOSS_CTAS_PER_SM", loss_min_blocks(p.units == p.V ? 0 : p.C, p.units * 8 == p.V ? 8 : 4));
+  int per_sm = env_int("DS_LOSS_CTAS_PER_SM", loss_min_blocks(p.units == p.V ? 0 : p.C, p.units * 8 == p.V ? 8 : 4));
+  if (p.use_tma) per_sm = env_int("DS_LOSS_TMA_CTAS_PER_SM", kTmaMinBlocks);
   int64_t grid = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
   const int64_t need = (p.n_steps + kWarps - 1) / kWarps;
   if (grid > need) grid = need;
@@ -55,7 +57,7 @@ int setup_tiles(LossParams& p, const char* who, bool stats) {
   return 0;
 }
 
-int setup_geometry(LossParams& p, int logit_dtype, bool* vec_out, const char* who, bool stats) {
+int setup_geometry(LossParams& p, int logit_dtype, int target_dtype, bool* vec_out, const char* who, bool stats) {
   const int C = p.C;
   const int W = (logit_dtype == DS_F32) ? 4 : (C <= 4 ? 8 : 4);
   bool vec = (p.V % W == 0) && aligned16(p.logits) && aligned16(p.dlogits) && aligned16(p.target) &&
@@ -63,12 +65,24 @@ int setup_geometry(LossParams& p, int logit_dtype, bool* vec_out, const char* wh
   if (env_int("DS_FORCE_SCALAR", 0)) vec = false;
   p.units = vec ? p.V / W : p.V;
   *vec_out = vec;
-  return setup_tiles(p, who, stats);
+  // TMA-staged shell (ds_loss_tma.cuh): vector path, statistics on, no separate Dice target, C in {2,3,4},
+  // every bulk copy a multiple of 16 bytes, one group of CTAs per instance.  Measured on B200
+  // (profiles/r01_notes/configs_*.log): it wins wherever a voxel costs many instructions per byte moved --
+  // half-precision logits, uint8 labels, C >= 3 (+12..14 %) -- and loses ~5 % on fp32 / int64 / C = 2, where
+  // the LDG shell's 32 warps per SM matter more than its exposed load latency.  DS_LOSS_TMA=0/1 overrides.
+  const bool eligible = vec && stats && !p.dice_target && C >= 2 && C <= 4 && (p.V % 16 == 0) &&
+                        p.B_local <= (int64_t)sm_count() * env_int("DS_LOSS_TMA_CTAS_PER_SM", kTmaMinBlocks);
+  const bool heavy = logit_dtype != DS_F32 || target_dtype != DS_I64 || C >= 3;
+  const int choice = env_int("DS_LOSS_TMA", -1);
+  p.use_tma = eligible && (choice < 0 ? heavy : choice != 0);
+  const int rc = setup_tiles(p, who, stats);
+  if (p.use_tma && p.groups != p.B_local) p.use_tma = 0;
+  return rc;
 }
 
 int launch_loss(LossParams& p, int logit_dtype, int target_dtype, bool grad, bool stats, cudaStream_t stream) {
   bool vec = false;
-  if (int rc = setup_geometry(p, logit_dtype, &vec, "loss_kernel", stats)) return rc;
+  if (int rc = setup_geometry(p, logit_dtype, target_dtype, &vec, "loss_kernel", stats)) return rc;
   switch (logit_dtype) {
     case DS_F32: return launch_loss_typed<float>(p, target_dtype, grad, stats, vec, stream);
     case DS_F16: return launch_loss_typed<__half>(p, target_dtype, grad, stats, vec, stream);

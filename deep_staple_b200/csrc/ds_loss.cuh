@@ -72,6 +72,7 @@ struct LossParams {
   int64_t weight_stride;        // kModeBwd: stride of inst_weight
   double nll_scale;             // fixed-point scale of the loss sums (power of two)
   int C, use_risk, mode, finalize, dp_outputs, grid, groups;
+  int use_tma;                           // launch the TMA-staged shell (ds_loss_tma.cuh)
   // fused multi-GPU exchange (ds_dp_loss_fwd_bwd_exchange): peer-mapped exchange buffers, see finish_launch
   const unsigned long long* peer_bases;  // device array [world]: base address of every rank's exchange buffer
   unsigned long long epoch;              // step counter, identical on all ranks, starts at 1
@@ -504,98 +505,7 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
 #pragma unroll
         for (int i = 0; i < VEC; ++i) td[i] = t[i];
       }
-      float gr[CC][VEC];
-      constexpr float kLog2e = 1.4426950408889634f;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const int ti = t[i];
-        const bool valid = (unsigned)ti < (unsigned)nc;  // anything else (e.g. torch's ignore_index) adds nothing
-        if constexpr (C == 2) {
-          // ---- binary fast path: softplus / sigmoid of d = z1 - z0 ------------------------------------
-          const float d = z[1][i] - z[0][i];
-          const bool am1 = d > 0.f;  // strict > : first maximum wins (:751)
-          const float a = fabsf(d);
-          const float e = ex2_approx(a * -kLog2e);  // exp(-|d|) in (0, 1]
-          const float inv = rcp_approx(1.0f + e);   // softmax of the maximal class
-          const bool t1 = ti == 1;
-          if (STATS) {
-            // log(1 + e) = 2 atanh(u), u = e / (2 + e) <= 1/3; odd series with a fitted tail
-            // (|rel err| < 2e-7 in fp32, relative -- confident voxels keep their tiny loss)
-            const float uu = e * rcp_approx(2.0f + e);
-            const float w = uu * uu;
-            float q = 1.3433776651e-01f;
-            q = fmaf(q, w, 1.4116977575e-01f);
-            q = fmaf(q, w, 2.0003835452e-01f);
-            q = fmaf(q, w, 3.3333319833e-01f);
-            const float u2 = uu + uu;
-            const float lse = fmaf(u2 * w, q, u2);
-            const float nll = lse + ((t1 != am1) ? a : 0.f);  // -log softmax(z)[t]  (:738)
-            nll_c[0] += (ti == 0) ? nll : 0.f;
-            nll_c[1] += t1 ? nll : 0.f;
-            pred_step[1] += am1 ? 1 : 0;
-            if constexpr (PACKED) {
-              const unsigned sh = (unsigned)ti * 8u + (am1 ? 16u : 0u);
-              hist += valid ? (1u << (sh & 31u)) : 0u;
-            } else {
-              lab_c[0] += (ti == 0) ? 1 : 0;
-              lab_c[1] += t1 ? 1 : 0;
-              tp_c[0] += (!am1 && td[i] == 0) ? 1 : 0;
-              tp_c[1] += (am1 && td[i] == 1) ? 1 : 0;
-            }
-          }
-          if (GRAD) {
-            float cf = uniform_coef ? coef0 : (t1 ? coef[1] : coef[0]);
-            cf = valid ? cf : 0.f;
-            const float p1 = am1 ? inv : e * inv;
-            const float g1 = fmaf(p1, cf, t1 ? -cf : 0.f);
-            gr[1][i] = g1;
-            gr[0][i] = -g1;
-          }
-        } else {
-          // ---- general class count -------------------------------------------------------------------
-          float m = z[0][i];
-          int am = 0;
-#pragma unroll
-          for (int c = 1; c < CC; ++c)
-            if (c < nc && z[c][i] > m) m = z[c][i], am = c;  // strict > : first maximum wins (:751)
-          float e[CC];
-          float rest = 0.f, zt = m;  // rest = sum of the non-maximal exp(z_c - max)
-#pragma unroll
-          for (int c = 0; c < CC; ++c) {
-            if (c < nc) {
-              e[c] = ex2_approx((z[c][i] - m) * kLog2e);  // exactly 1 for the maximum
-              rest += (c == am) ? 0.f : e[c];
-              zt = (ti == c) ? z[c][i] : zt;
-            }
-          }
-          if (STATS) {
-            const float nll = log1p_pos(rest) + (m - zt);  // -log softmax(z)[t]  (:738); only added where t == c
-#pragma unroll
-            for (int c = 0; c < CC; ++c) {
-              if (c < nc) {
-                nll_c[c] += (ti == c) ? nll : 0.f;
-                lab_c[c] += (ti == c) ? 1 : 0;
-                if (c > 0) pred_step[c] += (am == c) ? 1 : 0;
-                tp_c[c] += (am == c && td[i] == c) ? 1 : 0;
-              }
-            }
-          }
-          if (GRAD) {
-            float cf = 0.f;
-            if (uniform_coef) {
-              cf = valid ? coef0 : 0.f;
-            } else {
-#pragma unroll
-              for (int c = 0; c < CC; ++c)
-                if (c < nc) cf = (ti == c) ? coef[c] : cf;
-            }
-            const float cinv = cf * rcp_approx(1.0f + rest);
-#pragma unroll
-            for (int c = 0; c < CC; ++c)
-              if (c < nc) gr[c][i] = fmaf(e[c], cinv, (ti == c) ? -cf : 0.f);
-          }
-        }
-      }
+#include "ds_loss_math.inc"
       if (GRAD) {
 #pragma unroll
         for (int c = 0; c < CC; ++c) {

@@ -2,6 +2,7 @@
 #pragma once
 
 #include "ds_loss.cuh"
+#include "ds_loss_tma.cuh"
 
 namespace ds {
 
@@ -9,6 +10,19 @@ template <typename LT, typename TT, int C, int VEC>
 int launch_cfg(const LossParams& p, bool grad, bool stats, cudaStream_t stream) {
   const dim3 grid((unsigned)p.grid);
   const bool dice = stats && p.dice_target != nullptr;
+  if constexpr (C >= 2 && C <= 4 && VEC > 1) {
+    if (p.use_tma && stats && !dice) {
+      constexpr int smem = kTmaStages * tma_stage_bytes<LT, TT, C, VEC>();
+      auto launch = [&](auto kernel) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail((int)e, "loss_kernel_tma: %s", cudaGetErrorString(e));
+        kernel<<<grid, kThreads, smem, stream>>>(p);
+        count_launch();
+        return check_launch("loss_kernel_tma");
+      };
+      return grad ? launch(loss_kernel_tma<LT, TT, C, VEC, true>) : launch(loss_kernel_tma<LT, TT, C, VEC, false>);
+    }
+  }
   if (grad && stats) {
     if (dice) loss_kernel<LT, TT, C, VEC, true, true, true><<<grid, kThreads, 0, stream>>>(p);
     else loss_kernel<LT, TT, C, VEC, true, true, false><<<grid, kThreads, 0, stream>>>(p);

@@ -1,0 +1,244 @@
+// Fused loss, TMA-staged variant: the same math and the same exact statistics as ds::loss_kernel
+// (ds_loss.cuh), but global memory is read by the TMA engine instead of by the compute warps.
+//
+// Why: with LDG the compute warps alternate "issue loads -> wait ~1.5 us -> ~200 instructions", so
+// the bytes in flight per SM collapse whenever warps compute; half-precision / uint8 variants (fewer
+// bytes per voxel, same instruction count) end up far from the HBM roofline.  Here one elected thread
+// streams tiles into a ring of shared-memory stages with `cp.async.bulk` (1-D bulk copies completing
+// on an mbarrier): kStages - 1 tiles (C logit planes + labels each) are always in flight per CTA,
+// independent of what the warps are doing, and the warps only ever read shared memory.
+//
+//   tile    = kThreads x VEC consecutive voxels of one instance (one 128-bit piece per thread and plane)
+//   stage   = [plane 0 | ... | plane C-1 | labels] of one tile, 16 KB for fp32 / int64 / C = 2
+//   full[s] : mbarrier, 1 arrival (producer's expect_tx) + the bytes of the C + 1 bulk copies
+//   empty[s]: mbarrier, kWarps arrivals (one per warp once its lanes hold the stage in registers)
+//
+// Schedule: as in the LDG kernel one group of CTAs per instance (host guarantees groups == B_local
+// on this path); the CTAs of a group take the instance's tiles round-robin, so a group advances through
+// memory as one front.  Gradients go straight from registers to global memory (128-bit stores).
+#pragma once
+
+#include "ds_loss.cuh"
+
+namespace ds {
+
+#ifndef DS_TMA_STAGES
+#define DS_TMA_STAGES 4
+#endif
+#ifndef DS_TMA_MIN_BLOCKS
+#define DS_TMA_MIN_BLOCKS 2
+#endif
+constexpr int kTmaStages = DS_TMA_STAGES;
+constexpr int kTmaMinBlocks = DS_TMA_MIN_BLOCKS;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared (TMA), completion counted in bytes on `bar`; bytes % 16 == 0
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int BYTES>
+__device__ __forceinline__ void lds_raw(const void* p, Raw<BYTES>& r) {
+  if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < BYTES / 16; ++i) {
+      const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p) + 16 * i);
+      r.w[4 * i] = v.x, r.w[4 * i + 1] = v.y, r.w[4 * i + 2] = v.z, r.w[4 * i + 3] = v.w;
+    }
+  } else if constexpr (BYTES == 8) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    r.w[0] = v.x, r.w[1] = v.y;
+  } else {
+    static_assert(BYTES == 4, "unsupported shared-memory read width");
+    r.w[0] = *reinterpret_cast<const uint32_t*>(p);
+  }
+}
+
+template <typename LT, typename TT, int C, int VEC>
+constexpr int tma_stage_bytes() {
+  return kThreads * VEC * (C * (int)sizeof(LT) + (int)sizeof(TT));
+}
+
+// C in {2, 3, 4}; vector path only (V % VEC == 0, and V % 16 == 0 for uint8 labels so that every bulk
+// copy is a multiple of 16 bytes); no separate Dice target.
+template <typename LT, typename TT, int C, int VEC, bool GRAD>
+__global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const LossParams p) {
+  constexpr int CC = C;
+  constexpr bool STATS = true, DICE = false;
+  constexpr int nc = C;
+  constexpr int kTileV = kThreads * VEC;
+  constexpr int kPlaneBytes = kTileV * (int)sizeof(LT);
+  constexpr int kLabelBytes = kTileV * (int)sizeof(TT);
+  constexpr int kStageBytes = C * kPlaneBytes + kLabelBytes;
+  extern __shared__ __align__(128) unsigned char s_ring[];  // kTmaStages x kStageBytes
+  __shared__ __align__(8) uint64_t s_full[kTmaStages], s_empty[kTmaStages];
+  __shared__ double s_scratch[kWarps + 1];
+  __shared__ double s_mean;
+
+  const int lane = threadIdx.x & 31;
+  const int64_t V = p.V;
+  const bool uniform_coef = p.mode != kModeCE;
+  const double g = (GRAD && p.grad_scale) ? (double)__ldg(p.grad_scale) : 1.0;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], kWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  float coef[CC];
+#pragma unroll
+  for (int c = 0; c < CC; ++c) coef[c] = 0.f;
+  if (GRAD) {
+    if (p.mode == kModeDP) {
+      double ssum = 0.0;
+      for (int64_t i = threadIdx.x; i < p.B_total; i += kThreads) ssum += sigmoid_d(__ldg(p.bare_weight + i));
+      ssum = block_sum(ssum, s_scratch);
+      if (threadIdx.x == 0) s_mean = ssum / (double)p.B_total;
+    } else if (p.mode == kModeCE) {
+      double den = 0.0;
+      for (int c = 0; c < nc; ++c) den += (double)__ldg(p.class_w + c) * __ldg(p.class_counts + c);
+#pragma unroll
+      for (int c = 0; c < CC; ++c) coef[c] = (float)(g * (double)__ldg(p.class_w + c) / den);
+    }
+  }
+  __syncthreads();  // barriers initialised, s_mean published
+
+  // this CTA's instance and its tiles: j, j + G, j + 2G, ...
+  const int per_group = (int)gridDim.x / p.groups;
+  const int b = (int)blockIdx.x / per_group;
+  const int j0 = (int)blockIdx.x - b * per_group;
+  const int64_t n_tiles = (V + kTileV - 1) / kTileV;
+  const int64_t my_tiles = j0 < n_tiles ? (n_tiles - j0 + per_group - 1) / per_group : 0;
+
+  float coef0 = 0.f;
+  if (GRAD && p.mode != kModeCE) {
+    if (p.mode == kModeBwd) {
+      coef0 = (float)(g * (double)__ldg(p.bare_weight + b * p.weight_stride) / (double)V);
+    } else {
+      const int64_t bg = p.b_offset + b;
+      const double f = p.fixed_w ? (double)__ldg(p.fixed_w + bg) : 1.0;
+      coef0 = (float)(g * sigmoid_d(__ldg(p.bare_weight + bg)) / (s_mean * f) / (double)V);
+    }
+  }
+
+  const LT* __restrict__ zb = reinterpret_cast<const LT*>(p.logits) + (int64_t)b * nc * V;
+  LT* __restrict__ gb = reinterpret_cast<LT*>(p.dlogits) + (int64_t)b * nc * V;
+  const TT* __restrict__ tb = reinterpret_cast<const TT*>(p.target) + (int64_t)b * V;
+
+  // producer side (thread 0): fill stage (k % kTmaStages) with this CTA's k-th tile
+  auto produce = [&](int64_t k) {
+    const int s = (int)(k % kTmaStages);
+    const unsigned round = (unsigned)(k / kTmaStages);
+    if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1u);  // all warps hold the previous occupant in registers
+    const int64_t v0 = ((int64_t)j0 + k * per_group) * kTileV;
+    const int64_t nv = (V - v0) < kTileV ? (V - v0) : kTileV;
+    unsigned char* st = s_ring + (size_t)s * kStageBytes;
+    mbar_expect_tx(&s_full[s], (unsigned)(nv * (C * (int64_t)sizeof(LT) + (int64_t)sizeof(TT))));
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      tma_load_1d(st + c * kPlaneBytes, zb + (int64_t)c * V + v0, (unsigned)(nv * sizeof(LT)), &s_full[s]);
+    tma_load_1d(st + C * kPlaneBytes, tb + v0, (unsigned)(nv * sizeof(TT)), &s_full[s]);
+  };
+
+  constexpr bool PACKED = C == 2;
+  constexpr int kHistSteps = 252 / VEC;
+  long long nll_fix[CC];
+  int lab_c[CC], pred_c[CC], tp_c[CC];
+#pragma unroll
+  for (int c = 0; c < CC; ++c) nll_fix[c] = 0, lab_c[c] = 0, pred_c[c] = 0, tp_c[c] = 0;
+  const float nll_scale = (float)p.nll_scale;
+  unsigned hist = 0u;
+  int hist_steps = 0;
+  auto empty_hist = [&]() {  // fields: [t=0,am=0] [t=1,am=0] [t=0,am=1] [t=1,am=1]
+    const int h0 = hist & 0xffu, h1 = (hist >> 8) & 0xffu, h2 = (hist >> 16) & 0xffu, h3 = hist >> 24;
+    lab_c[0] += h0 + h2, lab_c[1] += h1 + h3, tp_c[0] += h0, tp_c[1] += h3;
+    hist = 0u, hist_steps = 0;
+  };
+
+  if (threadIdx.x == 0) {
+    const int64_t pre = my_tiles < kTmaStages - 1 ? my_tiles : kTmaStages - 1;
+    for (int64_t k = 0; k < pre; ++k) produce(k);
+  }
+
+  for (int64_t k = 0; k < my_tiles; ++k) {
+    if (threadIdx.x == 0 && k + kTmaStages - 1 < my_tiles) produce(k + kTmaStages - 1);
+    const int s = (int)(k % kTmaStages);
+    mbar_wait(&s_full[s], (unsigned)(k / kTmaStages) & 1u);
+    const int64_t v = ((int64_t)j0 + k * per_group) * kTileV + (int64_t)threadIdx.x * VEC;
+    const bool live = v < V;
+    const unsigned char* st = s_ring + (size_t)s * kStageBytes;
+    Raw<(int)sizeof(LT) * VEC> rz[CC];
+    Raw<(int)sizeof(TT) * VEC> rt;
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) lds_raw(st + c * kPlaneBytes + threadIdx.x * (VEC * (int)sizeof(LT)), rz[c]);
+      lds_raw(st + C * kPlaneBytes + threadIdx.x * (VEC * (int)sizeof(TT)), rt);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);  // this warp no longer needs the stage
+    if (live) {
+      float nll_c[CC];
+      int pred_step[CC];
+#pragma unroll
+      for (int c = 0; c < CC; ++c) nll_c[c] = 0.f, pred_step[c] = 0;
+      float z[CC][VEC];
+      int t[VEC], td[VEC];
+#pragma unroll
+      for (int c = 0; c < CC; ++c) Logit<LT>::template decode<VEC>(rz[c], z[c]);
+      Label<TT>::template decode<VEC>(rt, t);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) td[i] = t[i];
+#include "ds_loss_math.inc"
+      if (GRAD) {
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          Raw<(int)sizeof(LT) * VEC> out;
+          Logit<LT>::template encode<VEC>(gr[c], out);
+          store_raw(gb + (int64_t)c * V + v, out);
+        }
+      }
+      int others = 0;
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        nll_fix[c] += __float2ll_rn(nll_c[c] * nll_scale);
+        if (c > 0) others += pred_step[c], pred_c[c] += pred_step[c];
+      }
+      pred_c[0] += VEC - others;
+      if constexpr (PACKED) {
+        if (++hist_steps == kHistSteps) empty_hist();
+      }
+    }
+  }
+  if constexpr (PACKED) empty_hist();
+  flush_final<CC>(p, my_tiles > 0 ? b : -1, nll_fix, lab_c, pred_c, tp_c);
+  finish_launch(p, s_scratch);
+}
+
+}  // namespace ds
