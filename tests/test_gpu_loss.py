@@ -247,3 +247,57 @@ def test_invalid_arguments_raise(cuda_device):
         ds.dp_weighted_loss(torch.zeros((2, 9, 4, 4), device=cuda_device), t, torch.zeros(2, device=cuda_device))
     with pytest.raises(RuntimeError):
         ds.dp_weighted_loss(z.cpu(), t.cpu(), torch.zeros(2))
+
+
+def test_cuda_graph_capture_and_replay(cuda_device):
+    """The C-ABI calls allocate nothing and never synchronise: the fused loss + its backward glue can be
+    captured in a CUDA graph and replayed on new data (threading / streams)."""
+    import deep_staple_b200 as ds
+    from deep_staple_b200 import _binding as b
+
+    dev = cuda_device
+    lib = b.load()
+    gen = torch.Generator().manual_seed(3)
+    B, C, S = 4, 2, (16, 16, 16)
+    V = 16 ** 3
+    z = torch.zeros((B, C, *S), device=dev)
+    t = torch.zeros((B, *S), dtype=torch.long, device=dev)
+    bare = torch.randn(B, generator=gen).to(dev)
+    fixed = (torch.rand(B, generator=gen) + 1).to(dev)
+    cw = torch.tensor([0.7, 1.3], device=dev)
+    scale = torch.tensor(256.0, device=dev)
+    dl = torch.empty_like(z)
+    stats = torch.zeros((B, C, 4), dtype=torch.float64, device=dev)
+    loss_out = torch.zeros(2, device=dev)
+    d_bare = torch.zeros(B, device=dev)
+    per_inst = torch.zeros((B, 4), device=dev)
+    ws = torch.zeros((int(lib.ds_dp_loss_workspace_bytes(B, C)) + 7) // 8, dtype=torch.int64, device=dev)
+
+    def launch():
+        rc = lib.ds_dp_loss_fwd_bwd(z.data_ptr(), b.DS_F32, t.data_ptr(), b.DS_I64, None, B, C, V, bare.data_ptr(),
+                                    fixed.data_ptr(), B, 0, cw.data_ptr(), 1, scale.data_ptr(), dl.data_ptr(),
+                                    stats.data_ptr(), loss_out.data_ptr(), d_bare.data_ptr(), per_inst.data_ptr(),
+                                    ws.data_ptr(), ws.numel() * 8, torch.cuda.current_stream(dev).cuda_stream)
+        assert rc == 0
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        launch()  # warm-up outside the capture
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        launch()
+    for seed in (10, 11):
+        g2 = torch.Generator().manual_seed(seed)
+        logits = 2 * torch.randn((B, C, *S), generator=g2)
+        target = (torch.rand((B, *S), generator=g2) < 0.3).long()
+        z.copy_(logits)
+        t.copy_(target)
+        graph.replay()
+        torch.cuda.synchronize()
+        zz = z.clone().requires_grad_(True)
+        ref = ds.dp_weighted_loss(zz, t, bare, fixed, True, grad_scaler=256.0, class_weights=cw, return_all=True)
+        (ref.dp_loss * 256.0).backward()
+        assert torch.equal(loss_out[0], ref.dp_loss.detach()) and torch.equal(stats, ref.inst_stats)
+        assert torch.equal(dl, zz.grad)
