@@ -467,55 +467,55 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     hist = 0u, hist_steps = 0;
   };
 
-  // ---- step schedule: group range, interleaved among the group's warps ---------------------------
-  const StepWalk walk(p);
-  int cur_b = -1;
+  // fast binary path (all labels of a warp step in {0,1}): three plain counters instead of the histogram
+  int n_t1 = 0, n_am1 = 0, n_both = 0, seen_fast = 0;
+  auto merge_fast = [&]() {
+    lab_c[1] += n_t1, lab_c[0] += seen_fast - n_t1;
+    tp_c[1] += n_both, tp_c[0] += seen_fast - n_t1 - n_am1 + n_both;
+    pred_c[1] += n_am1, pred_c[0] += seen_fast - n_am1;
+    n_t1 = n_am1 = n_both = seen_fast = 0;
+  };
+
+  // ---- one warp step: VEC voxels per lane at element offset `off` of the instance -----------------
   float coef0 = 0.f;
-  int b = walk.b0;
-  int64_t s_in = walk.s_in0;  // step inside instance b
-  for (int64_t step = walk.first; step < walk.hi; step += walk.stride, s_in += walk.stride) {
-    while (s_in >= p.steps_per_inst) s_in -= p.steps_per_inst, ++b;
-    const int64_t u = s_in * 32 + lane;
-    if (b != cur_b) {
-      if (STATS && cur_b >= 0) {
-        if constexpr (PACKED) empty_hist();
-        flush_instance<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c);
-      }
-      cur_b = b;
-      coef0 = instance_coef(b);
+  auto process = [&](const LT* __restrict__ zb, const TT* __restrict__ tb, const TT* __restrict__ db,
+                     LT* __restrict__ gb, auto off) {
+    float z[CC][VEC];
+    int t[VEC], td[VEC];
+#pragma unroll
+    for (int c = 0; c < CC; ++c)
+      if (c < nc) load_logits<LT, VEC>((zb + (int64_t)c * V) + off, z[c]);
+    load_labels<TT, VEC>(tb + off, t);
+    if constexpr (STATS && DICE) {
+      load_labels<TT, VEC>(db + off, td);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) td[i] = t[i];
     }
-    if (u < p.units) {
-      const int64_t v = u * VEC;
-      const LT* __restrict__ pz = reinterpret_cast<const LT*>(p.logits) + (int64_t)b * nc * V + v;
-      LT* __restrict__ pg = reinterpret_cast<LT*>(p.dlogits) + (int64_t)b * nc * V + v;
-      const TT* __restrict__ pt = reinterpret_cast<const TT*>(p.target) + (int64_t)b * V + v;
+    float gr[CC][VEC];
+    bool fast = false;
+    if constexpr (C == 2 && !DICE) {
+      unsigned any = 0u;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) any |= (unsigned)t[i];
+      fast = !__any_sync(__activemask(), any > 1u);
+    }
+    if (fast) {
+      if constexpr (C == 2 && !DICE) {
+        float nll_all = 0.f, nll_one = 0.f;
+#include "ds_loss_math_bin.inc"
+        if (STATS) {
+          const long long f_all = __float2ll_rn(nll_all * nll_scale), f_one = __float2ll_rn(nll_one * nll_scale);
+          nll_fix[0] += f_all - f_one, nll_fix[1] += f_one;
+          seen_fast += VEC;
+        }
+      }
+    } else {
       float nll_c[CC];
       int pred_step[CC];
 #pragma unroll
       for (int c = 0; c < CC; ++c) nll_c[c] = 0.f, pred_step[c] = 0;
-      float z[CC][VEC];
-      int t[VEC], td[VEC];
-#pragma unroll
-      for (int c = 0; c < CC; ++c)
-        if (c < nc) load_logits<LT, VEC>(pz + (int64_t)c * V, z[c]);
-      load_labels<TT, VEC>(pt, t);
-      if constexpr (STATS && DICE) {
-        load_labels<TT, VEC>(reinterpret_cast<const TT*>(p.dice_target) + (int64_t)b * V + v, td);
-      } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) td[i] = t[i];
-      }
 #include "ds_loss_math.inc"
-      if (GRAD) {
-#pragma unroll
-        for (int c = 0; c < CC; ++c) {
-          if (c < nc) {
-            Raw<(int)sizeof(LT) * VEC> out;
-            Logit<LT>::template encode<VEC>(gr[c], out);
-            store_raw(pg + (int64_t)c * V, out);
-          }
-        }
-      }
       if (STATS) {
         // this lane's fp32 loss sums of the step (fixed voxels, fixed order) become exact integers
         int others = 0;
@@ -532,9 +532,71 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
         }
       }
     }
+    if (GRAD) {
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        if (c < nc) {
+          Raw<(int)sizeof(LT) * VEC> out;
+          Logit<LT>::template encode<VEC>(gr[c], out);
+          store_raw((gb + (int64_t)c * V) + off, out);
+        }
+      }
+    }
+  };
+  auto flush = [&](int b) {
+    if constexpr (PACKED) empty_hist();
+    merge_fast();
+    flush_instance<CC>(p, b, nll_fix, lab_c, pred_c, tp_c);
+  };
+
+  // ---- step schedule: group range, interleaved among the group's warps ---------------------------
+  int cur_b = -1;
+  if (p.groups == p.B_local && V < 0x70000000LL) {
+    // one group per instance (the normal case): the instance is a CTA-uniform value, the base pointers
+    // live in uniform registers and a 32-bit voxel offset is all a lane carries from step to step
+    const int per_group = (int)gridDim.x / p.groups;
+    const int b = (int)blockIdx.x / per_group;
+    const unsigned wg = (unsigned)((int)blockIdx.x - b * per_group) * kWarps + (threadIdx.x >> 5);
+    const unsigned stride = (unsigned)per_group * kWarps;
+    const unsigned n_steps = (unsigned)p.steps_per_inst;
+    const LT* __restrict__ zb = reinterpret_cast<const LT*>(p.logits) + (int64_t)b * nc * V;
+    LT* __restrict__ gb = reinterpret_cast<LT*>(p.dlogits) + (int64_t)b * nc * V;
+    const TT* __restrict__ tb = reinterpret_cast<const TT*>(p.target) + (int64_t)b * V;
+    const TT* __restrict__ db = DICE ? reinterpret_cast<const TT*>(p.dice_target) + (int64_t)b * V : nullptr;
+    const unsigned n_vox = (unsigned)V, dv = stride * 32u * VEC;
+    unsigned off = (wg * 32u + lane) * VEC;
+    if (wg < n_steps) {
+      cur_b = b;
+      coef0 = instance_coef(b);
+    }
+    for (unsigned s = wg; s < n_steps; s += stride, off += dv)
+      if (off < n_vox) process(zb, tb, db, gb, off);
+  } else {
+    const StepWalk walk(p);
+    int b = walk.b0;
+    int64_t s_in = walk.s_in0;  // step inside instance b
+    const LT* __restrict__ zb = nullptr;
+    LT* __restrict__ gb = nullptr;
+    const TT* __restrict__ tb = nullptr;
+    const TT* __restrict__ db = nullptr;
+    for (int64_t step = walk.first; step < walk.hi; step += walk.stride, s_in += walk.stride) {
+      while (s_in >= p.steps_per_inst) s_in -= p.steps_per_inst, ++b;
+      if (b != cur_b) {
+        if (STATS && cur_b >= 0) flush(cur_b);
+        cur_b = b;
+        coef0 = instance_coef(b);
+        zb = reinterpret_cast<const LT*>(p.logits) + (int64_t)b * nc * V;
+        gb = reinterpret_cast<LT*>(p.dlogits) + (int64_t)b * nc * V;
+        tb = reinterpret_cast<const TT*>(p.target) + (int64_t)b * V;
+        if constexpr (DICE) db = reinterpret_cast<const TT*>(p.dice_target) + (int64_t)b * V;
+      }
+      const int64_t u = s_in * 32 + lane;
+      if (u < p.units) process(zb, tb, db, gb, u * VEC);
+    }
   }
   if (STATS) {
     if constexpr (PACKED) empty_hist();
+    merge_fast();
     flush_final<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c);
     finish_launch(p, s_scratch);
   }

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   const float nll_scale = (float)p.nll_scale;
   unsigned hist = 0u;
   int hist_steps = 0;
+  int n_t1 = 0, n_am1 = 0, n_both = 0, seen_fast = 0;  // fast binary path counters (ds_loss_math_bin.inc)
   auto empty_hist = [&]() {  // fields: [t=0,am=0] [t=1,am=0] [t=0,am=1] [t=1,am=1]
     const int h0 = hist & 0xffu, h1 = (hist >> 8) & 0xffu, h2 = (hist >> 16) & 0xffu, h3 = hist >> 24;
     lab_c[0] += h0 + h2, lab_c[1] += h1 + h3, tp_c[0] += h0, tp_c[1] += h3;
@@ -204,10 +205,6 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[s]);  // this warp no longer needs the stage
     if (live) {
-      float nll_c[CC];
-      int pred_step[CC];
-#pragma unroll
-      for (int c = 0; c < CC; ++c) nll_c[c] = 0.f, pred_step[c] = 0;
       float z[CC][VEC];
       int t[VEC], td[VEC];
 #pragma unroll
@@ -215,7 +212,39 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
       Label<TT>::template decode<VEC>(rt, t);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) td[i] = t[i];
+      float gr[CC][VEC];
+      bool fast = false;
+      if constexpr (C == 2) {
+        unsigned any = 0u;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) any |= (unsigned)t[i];
+        fast = !__any_sync(__activemask(), any > 1u);
+      }
+      if (fast) {
+        if constexpr (C == 2) {
+          float nll_all = 0.f, nll_one = 0.f;
+#include "ds_loss_math_bin.inc"
+          const long long f_all = __float2ll_rn(nll_all * nll_scale), f_one = __float2ll_rn(nll_one * nll_scale);
+          nll_fix[0] += f_all - f_one, nll_fix[1] += f_one;
+          seen_fast += VEC;
+        }
+      } else {
+        float nll_c[CC];
+        int pred_step[CC];
+#pragma unroll
+        for (int c = 0; c < CC; ++c) nll_c[c] = 0.f, pred_step[c] = 0;
 #include "ds_loss_math.inc"
+        int others = 0;
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          nll_fix[c] += __float2ll_rn(nll_c[c] * nll_scale);
+          if (c > 0) others += pred_step[c], pred_c[c] += pred_step[c];
+        }
+        pred_c[0] += VEC - others;
+        if constexpr (PACKED) {
+          if (++hist_steps == kHistSteps) empty_hist();
+        }
+      }
       if (GRAD) {
 #pragma unroll
         for (int c = 0; c < CC; ++c) {
@@ -224,19 +253,12 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
           store_raw(gb + (int64_t)c * V + v, out);
         }
       }
-      int others = 0;
-#pragma unroll
-      for (int c = 0; c < CC; ++c) {
-        nll_fix[c] += __float2ll_rn(nll_c[c] * nll_scale);
-        if (c > 0) others += pred_step[c], pred_c[c] += pred_step[c];
-      }
-      pred_c[0] += VEC - others;
-      if constexpr (PACKED) {
-        if (++hist_steps == kHistSteps) empty_hist();
-      }
     }
   }
   if constexpr (PACKED) empty_hist();
+  lab_c[1] += n_t1, lab_c[0] += seen_fast - n_t1;
+  tp_c[1] += n_both, tp_c[0] += seen_fast - n_t1 - n_am1 + n_both;
+  pred_c[1] += n_am1, pred_c[0] += seen_fast - n_am1;
   flush_final<CC>(p, my_tiles > 0 ? b : -1, nll_fix, lab_c, pred_c, tp_c);
   finish_launch(p, s_scratch);
 }
