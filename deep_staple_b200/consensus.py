@@ -200,6 +200,55 @@ def consensus_multiclass(labels: torch.Tensor, data_parameters: torch.Tensor, nu
     return out
 
 
+def _sorted_unique(ind: torch.Tensor, shape) -> bool:
+    """True if COO indices ``[ndim, nnz]`` are strictly increasing in row-major order, i.e. the tensor
+    is coalesced even if its flag says otherwise (``torch.stack`` of coalesced tensors, as written by
+    main_deep_staple.py:1025-1027, produces exactly that).  O(nnz), no sort."""
+    if ind.shape[1] < 2:
+        return True
+    lin = torch.zeros(ind.shape[1], dtype=torch.int64, device=ind.device)
+    for d, size in enumerate(shape):
+        lin = lin * int(size) + ind[d]
+    return bool((lin[1:] > lin[:-1]).all())
+
+
+def _coalesced_parts(st: torch.Tensor):
+    """(indices, values) of a sparse COO tensor in coalesced order, sorting only when really needed."""
+    if st.is_coalesced():
+        return st.indices(), st.values()
+    ind, val = st._indices(), st._values()
+    if _sorted_unique(ind, st.shape):
+        return ind, val
+    st = st.coalesce()
+    return st.indices(), st.values()
+
+
+class _SparseRows:
+    """``stacked[k]`` for a stacked sparse-COO tensor ``[K, *S]`` in O(nnz of row k): torch's own
+    sparse indexing scans all stored elements for every row, which makes the notebook's grouping loop
+    (consensus.ipynb:353-377) quadratic in the snapshot size.  Rows come out as coalesced sparse
+    tensors with the same indices / values ``stacked[k]`` would give."""
+
+    def __init__(self, stacked: torch.Tensor):
+        self.dense = None
+        if not (isinstance(stacked, torch.Tensor) and stacked.is_sparse):
+            self.dense = stacked
+            return
+        self.shape = tuple(stacked.shape[1:])
+        ind, self.val = _coalesced_parts(stacked)
+        counts = torch.bincount(ind[0], minlength=stacked.shape[0])
+        self.ends = torch.cumsum(counts, 0).tolist()
+        self.rest = ind[1:]
+
+    def __getitem__(self, k: int) -> torch.Tensor:
+        if self.dense is not None:
+            return self.dense[k]
+        lo = self.ends[k - 1] if k > 0 else 0
+        hi = self.ends[k]
+        return torch.sparse_coo_tensor(self.rest[:, lo:hi], self.val[lo:hi], self.shape, is_coalesced=True,
+                                       check_invariants=False)
+
+
 def group_snapshot(snapshot: Dict) -> Dict[str, Dict]:
     """consensus.ipynb:353-377: group the snapshot by fixed (target) id.  Ids look like
     ``'126l:m102l'``: fixed id ``_id[:4]``, moving (atlas) id ``_id[6:]``; the first entry of a fixed
@@ -208,31 +257,116 @@ def group_snapshot(snapshot: Dict) -> Dict[str, Dict]:
     first_index = {}
     for k, _id in enumerate(d_ids):
         first_index.setdefault(_id, k)  # the notebook uses d_ids.index(_id): first occurrence
+    labels, preds = _SparseRows(snapshot["labels"]), _SparseRows(snapshot["train_predictions"])
+    mods = _SparseRows(snapshot["modified_labels"])
     consensus_dicts: Dict[str, Dict] = {}
     for _id in d_ids:
         k = first_index[_id]
         f_id, m_id = _id[:4], _id[6:]
         fixed = consensus_dicts.get(f_id)
         if fixed is None:
-            fixed = {"expert_label": snapshot["labels"][k], "prediction": snapshot["train_predictions"][k]}
+            fixed = {"expert_label": labels[k], "prediction": preds[k]}
         moving = fixed.get(m_id, {})
-        moving["warped_label"] = snapshot["modified_labels"][k]
+        moving["warped_label"] = mods[k]
         moving["data_parameter"] = snapshot["data_parameters"][k]
         fixed[m_id] = moving
         consensus_dicts[f_id] = fixed
     return consensus_dicts
 
 
+def _batched_snapshot_vote(snapshot, dicts, dev):
+    """All targets of a snapshot in ONE vote launch straight from the stacked sparse-COO
+    ``modified_labels [K, *S]`` (no per-candidate tensors, no densification): returns
+    ``(maps uint8 [T, V] on dev, order of the fixed ids)`` or ``None`` when the targets do not all have
+    the same number of candidates (then the caller votes target by target)."""
+    mod = snapshot["modified_labels"]
+    if not (isinstance(mod, torch.Tensor) and mod.is_sparse):
+        return None
+    d_ids = list(snapshot["d_ids"])
+    first = {}
+    for k, _id in enumerate(d_ids):
+        first.setdefault(_id, k)
+    row_of: Dict[str, Dict[str, int]] = {}  # same insertion / overwrite order as group_snapshot
+    for _id in d_ids:
+        row_of.setdefault(_id[:4], {})[_id[6:]] = first[_id]
+    f_ids = list(dicts.keys())
+    rows = [list(row_of[f_id].values()) for f_id in f_ids]  # snapshot rows in (target, candidate) order
+    n = len(rows[0])
+    if n == 0 or any(len(r) != n for r in rows):
+        return None
+    T = len(rows)
+    shape = tuple(mod.shape[1:])
+    V = 1
+    for d in shape:
+        V *= d
+    ind, val = _coalesced_parts(mod.to(dev))  # sortedness check / sort on the GPU
+    val = val.to(torch.int64)
+    strides = []
+    acc = 1
+    for d in reversed(shape):
+        strides.append(acc)
+        acc *= d
+    strides = torch.tensor(list(reversed(strides)), dtype=torch.int64, device=dev)
+    lin = (ind[1:] * strides[:, None]).sum(0)  # linear voxel index; sorted inside every instance (coalesced)
+    K = mod.shape[0]
+    counts = torch.bincount(ind[0], minlength=K)
+    starts = torch.cumsum(counts, 0) - counts
+    order = torch.tensor([r for row in rows for r in row], dtype=torch.int64, device=dev)
+    seg_len = counts[order]
+    seg_off = torch.zeros(T * n + 1, dtype=torch.int64, device=dev)
+    seg_off[1:] = torch.cumsum(seg_len, 0)
+    total = int(seg_off[-1])
+    # gather the stored elements into (target, candidate) segment order
+    src = torch.repeat_interleave(starts[order] - seg_off[:-1], seg_len) + torch.arange(total, device=dev)
+    voxel_index = lin[src].contiguous()
+    values = val[src].contiguous()
+    dps = snapshot["data_parameters"].detach().reshape(-1).to(device=dev, dtype=torch.float32)[order].reshape(T, n).contiguous()
+    out = torch.empty((T, V), dtype=torch.uint8, device=dev)
+    lib = _b.load()
+    with torch.cuda.device(dev):
+        rc = lib.ds_consensus_vote_sparse(_b.ptr(voxel_index), _b.ptr(values), _b.ptr(seg_off), _b.ptr(dps), 1, T, n, V,
+                                          _b.ptr(out), _b.DS_U8, None, _b.stream_ptr(dev))
+    _b.check(rc, "ds_consensus_vote_sparse")
+    return out, f_ids, shape
+
+
 def consensus_from_snapshot(snapshot, *, device=None, with_dice: bool = True) -> Dict[str, Dict]:
     """The consensus driver cell (consensus.ipynb:353-418) minus the SimpleITK STAPLE baseline:
     ``snapshot`` is the dict saved as ``train_label_snapshot.pth`` (main_deep_staple.py:963-1037) or
     a path to it.  Per target: vote over all its registered candidates, Dice against the expert label,
-    results stored under ``dp_consensus`` (sparse, like the notebook) / ``dp_consensus_oracle_dice``."""
+    results stored under ``dp_consensus`` (sparse, like the notebook) / ``dp_consensus_oracle_dice``.
+
+    When every target has the same number of candidates (the reference's data: N atlases per target)
+    the whole snapshot is voted on in one launch from the stacked sparse labels and the Dice counts of
+    all targets come from one more launch; otherwise the targets are processed one by one."""
     if isinstance(snapshot, (str, bytes)) or hasattr(snapshot, "__fspath__"):
         from .snapshot import load_snapshot
 
         snapshot = load_snapshot(snapshot)
     dicts = group_snapshot(snapshot)
+    dev = _cuda_device(device)
+    batched = _batched_snapshot_vote(snapshot, dicts, dev)
+    if batched is not None:
+        maps, f_ids, shape = batched
+        T = len(f_ids)
+        dice = None
+        if with_dice:
+            from .loss import label_statistics
+            from .metrics import dice_from_stats
+
+            experts = []
+            for f_id in f_ids:
+                e = dicts[f_id]["expert_label"]
+                experts.append((e.to(dev).to_dense() if e.is_sparse else e.to(dev)).reshape(-1).to(torch.uint8))
+            stats = label_statistics(maps, torch.stack(experts), 2)
+            dice = dice_from_stats(stats, nan_for_unlabeled_target=False)  # CPU [T, 2]
+        for i, f_id in enumerate(f_ids):
+            sp = maps[i].reshape(shape).to_sparse()
+            dicts[f_id]["dp_consensus"] = torch.sparse_coo_tensor(sp.indices(), sp.values().long(), shape, is_coalesced=True,
+                                                                check_invariants=False).cpu()
+            if dice is not None:
+                dicts[f_id]["dp_consensus_oracle_dice"] = dice[i : i + 1]
+        return dicts
     for f_id, fixed in dicts.items():
         entries = [e for e in fixed.values() if isinstance(e, dict)]
         lbls: List[torch.Tensor] = [e["warped_label"] for e in entries]
