@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 import torch
 
@@ -54,6 +54,8 @@ SIGNATURES = {
     "ds_dp_loss_backward_logits": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p,
                                            c_int64, c_void_p, c_void_p, c_void_p]),
     "ds_rescale_inplace": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "ds_sparse_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                    c_double, c_double, c_double, c_double, c_void_p]),
     "ds_label_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                c_size_t, c_void_p]),
 }

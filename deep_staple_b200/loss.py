@@ -82,6 +82,7 @@ class DPLossOutput:
     fg_pred: torch.Tensor  # [B]  n_b = #voxels predicted foreground                         (:751)
     instance_weight: torch.Tensor  # [B]  w_b                                                (:743-748)
     inst_stats: torch.Tensor  # [B, C, 4] float64: sum-nll / label / pred / TP counts (hard-Dice statistics)
+    d_bare_weight: Optional[torch.Tensor] = None  # [B] d(scale * dp_loss)/d(bare_weight), for optim.dp_optimizer_step
 
 
 class _DPLoss(torch.autograd.Function):
@@ -122,11 +123,11 @@ class _DPLoss(torch.autograd.Function):
         ctx.assumed = scale
         ctx.save_for_backward(d_bare, dlogits)
         ce, pi = loss_out[1], per_inst
-        ctx.mark_non_differentiable(ce, pi, inst_stats)
-        return loss_out[0], ce, pi, inst_stats
+        ctx.mark_non_differentiable(ce, pi, inst_stats, d_bare)
+        return loss_out[0], ce, pi, inst_stats, d_bare
 
     @staticmethod
-    def backward(ctx, grad_loss, _g_ce, _g_pi, _g_stats):
+    def backward(ctx, grad_loss, _g_ce, _g_pi, _g_stats, _g_d):
         d_bare, dlogits = ctx.saved_tensors
         assumed = ctx.assumed
         g = grad_loss.detach().to(torch.float32).reshape(())
@@ -179,7 +180,7 @@ def dp_weighted_loss(
         embedding, idx = bare_weight
         bare_weight = embedding(idx).squeeze()  # :741 (sparse=True embedding -> sparse grad)
     scale = _scale_tensor(grad_scaler, dp_logits.device)
-    loss, ce, per_inst, stats = _DPLoss.apply(
+    loss, ce, per_inst, stats, d_bare = _DPLoss.apply(
         dp_logits, bare_weight, b_seg_modified, fixed_weighting, bool(use_risk_regularization), scale,
         class_weights, dice_target,
     )
@@ -187,7 +188,7 @@ def dp_weighted_loss(
         return loss
     return DPLossOutput(
         dp_loss=loss, ce_loss=ce, per_instance_ce=per_inst[:, _b.DS_INST_CE], fg_pred=per_inst[:, _b.DS_INST_FG],
-        instance_weight=per_inst[:, _b.DS_INST_WEIGHT], inst_stats=stats,
+        instance_weight=per_inst[:, _b.DS_INST_WEIGHT], inst_stats=stats, d_bare_weight=d_bare,
     )
 
 

@@ -225,6 +225,21 @@ int ds_rescale_inplace(void* x, int dtype, int64_t n, const float* numer, const 
                        ds_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused data-parameter optimiser step
+ *   replaces  scaler_dp.step(optimizer_dp)                       main_deep_staple.py:764-773
+ *             = GradScaler unscale + inf check + SparseAdam.step  (:442-445; torch/optim/_functional.py:sparse_adam)
+ * for the [M, 1] embedding of :418.  One launch on the B touched rows:
+ *   g = grad * float(1 / double(scale));  any non-finite g -> *found_inf = 1 and NOTHING is updated;
+ *   m += (g - m)(1 - b1);  v += (g^2 - v)(1 - b2);  w -= step_size * m_new / (sqrt(v_new) + eps)
+ * with step_size = lr * sqrt(1 - b2^step) / (1 - b1^step) formed by the caller (python float math, as torch does).
+ * idx must not contain duplicates (SubsetRandomSampler, main_deep_staple.py:597).  grad is d_bare_weight
+ * as written by ds_dp_loss_fwd_bwd (already multiplied by the GradScaler scale); scale may be NULL (= 1).
+ * ------------------------------------------------------------------------------------------- */
+int ds_sparse_adam_step(float* weight, float* exp_avg, float* exp_avg_sq, const int64_t* idx, const float* grad,
+                        int64_t B, int64_t M, const float* scale, float* found_inf, double beta1, double beta2,
+                        double eps, double step_size, ds_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Label statistics (per-fold pre-pass and hard Dice)
  *   replaces  torch.bincount(...) / (mod_label > 0).sum()      main_deep_staple.py:646, 648
  *             _diceNd counting loop                              deep_staple/metrics.py:93-101
