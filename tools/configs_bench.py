@@ -75,6 +75,39 @@ def vote_case(name, T, N, S, dt, steps=20, nsets=1):
           f"({T * N * V / sec / 1e9:7.1f} Gvox-cand/s)", flush=True)
 
 
+def aten_cuda_case(name, B, C, S, ldt, steps=10):
+    """Secondary baseline: the reference's own lines (main_deep_staple.py:738-762) on CUDA tensors, i.e. the
+    stock ATen kernel composition on the same B200 (fwd + backward into logits and data parameters)."""
+    from torch import nn
+
+    V = math.prod(S)
+    g = torch.Generator(device=dev).manual_seed(0)
+    z0 = (2 * torch.randn((B, C, *S), generator=g, device=dev)).to(ldt)
+    t = (torch.rand((B, *S), generator=g, device=dev) * C * 0.35).long().clamp_(0, C - 1)
+    emb = nn.Embedding(600, 1, sparse=True).to(dev)
+    idx = torch.arange(B, device=dev)
+    fixed = torch.rand(600, device=dev) + 1
+    n_dims = tuple(range(-len(S), 0))
+
+    def fn():
+        z = z0.detach().requires_grad_(True)
+        zz = z.float()
+        dp_loss = nn.CrossEntropyLoss(reduction="none")(zz, t).mean(n_dims)
+        weight = torch.sigmoid(emb(idx).squeeze())
+        weight = weight / weight.mean()
+        weight = weight / fixed[idx]
+        p_pred_num = (zz.argmax(1) > 0).sum(dim=n_dims).detach()
+        risk = -weight * p_pred_num / V
+        loss = (dp_loss * weight).sum() + risk.sum()
+        (loss * 1024.0).backward()
+        emb.weight.grad = None
+
+    sec = bench.timed(fn, steps, 3) / steps
+    alg = B * V * (2 * C * z0.element_size() + 8)
+    print(f"{name:44s} {sec * 1e6:9.1f} us  {alg / sec / 1e9:8.1f} GB/s  frac {alg / sec / 1e9 / peak:5.3f}  "
+          f"({B * V / sec / 1e9:7.1f} Gvox/s)  [stock torch CUDA composition]", flush=True)
+
+
 if __name__ == "__main__":
     S3 = (128, 128, 128)
     loss_case("cfg2 fp32/int64 fwd+bwd", 8, 2, S3, torch.float32, torch.int64)
@@ -89,6 +122,8 @@ if __name__ == "__main__":
     loss_case("cfg5 8x3x192x160x160 fp32/int64", 8, 3, (192, 160, 160), torch.float32, torch.int64, nsets=2, steps=50)
     loss_case("cfg5 1x3x192x160x160 fp32/int64 (B=1)", 1, 3, (192, 160, 160), torch.float32, torch.int64, nsets=3)
     loss_case("4-class 8x4x128^3 fp32/int64", 8, 4, S3, torch.float32, torch.int64, nsets=2, steps=100)
+    aten_cuda_case("ATen-on-B200 cfg2 fp32/int64 fwd+bwd", 8, 2, S3, torch.float32)
+    aten_cuda_case("ATen-on-B200 cfg2 fp16/int64 fwd+bwd", 8, 2, S3, torch.float16)
     vote_case("cfg1 vote 1x10x128^3 int64", 1, 10, S3, torch.int64, steps=200, nsets=4)
     vote_case("cfg1 vote 1x10x128^3 uint8", 1, 10, S3, torch.uint8, steps=200, nsets=12)
     vote_case("cfg3 shard 13x30x128^3 int64", 13, 30, S3, torch.int64)
