@@ -36,10 +36,11 @@
 namespace ds {
 
 constexpr int kStatsPerClass = DS_STATS;
-// workspace header: two-level arrival tickets (same-address atomics serialise at the L2, so ~600 CTAs
-// do not all knock on one counter).  Level 1: kTickets1 counters, 128 B apart (CTA i arrives at
-// counter i % kTickets1); the last arriver of each goes on to level 2.
+// workspace header: arrival tickets.  Big grids use two levels (same-address atomics serialise at the
+// L2): level 1 = kTickets1 counters, 128 B apart (CTA i arrives at counter i % kTickets1), the last
+// arriver of each goes on to level 2; grids of one persistent wave use the level-2 counter alone.
 constexpr int kTickets1 = 32;
+constexpr int kSingleTicketGrid = 2048;  // up to this many CTAs a single arrival counter is used
 constexpr int kTicketStride = 32;                                  // words (128 B)
 constexpr int kWsCounters = (1 + kTickets1) * kTicketStride;       // [0] level 2, [32 * (1 + i)] level 1
 
@@ -73,6 +74,7 @@ struct LossParams {
   double nll_scale;             // fixed-point scale of the loss sums (power of two)
   int C, use_risk, mode, finalize, dp_outputs, grid, groups;
   int use_tma;                           // launch the TMA-staged shell (ds_loss_tma.cuh)
+  const double* stats_smem;              // device-side only: statistics staged in shared memory for the epilogue
   // fused multi-GPU exchange (ds_dp_loss_fwd_bwd_exchange): peer-mapped exchange buffers, see finish_launch
   const unsigned long long* peer_bases;  // device array [world]: base address of every rank's exchange buffer
   unsigned long long epoch;              // step counter, identical on all ranks, starts at 1
@@ -123,17 +125,40 @@ __device__ __forceinline__ float log1p_pos(float r) {
   return fmaf((float)k, 0.69314718056f, f + y);
 }
 
+// The epilogue reads the reduced statistics from shared memory when the finishing CTA staged them there
+// (single-GPU launches with B * C * 4 <= kSmemStats), else through L2 from the inst_stats array.
+constexpr int kSmemStats = 1024;
+__device__ __forceinline__ double load_stat(const LossParams& p, int64_t i) {
+  return p.stats_smem ? p.stats_smem[i] : __ldcg(p.inst_stats + i);
+}
+
+// Mean sigmoid of the batch's data parameters (:744) for the gradient coefficient, in fp32.  Small
+// batches (every configuration of the reference) are handled by each warp on its own -- no shared
+// memory, no block barrier in the prologue; big batches fall back to one block-wide sum.
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float batch_mean_sigmoid(const LossParams& p, double* scratch) {
+  const int lane = threadIdx.x & 31;
+  if (p.B_total <= 64) {
+    float s = 0.f;
+    for (int i = lane; i < (int)p.B_total; i += 32) s += sigmoid_f(__ldg(p.bare_weight + i));
+    return warp_sum(s) / (float)p.B_total;
+  }
+  double ssum = 0.0;
+  for (int64_t i = threadIdx.x; i < p.B_total; i += kThreads) ssum += (double)sigmoid_f(__ldg(p.bare_weight + i));
+  return (float)(block_sum(ssum, scratch) / (double)p.B_total);
+}
+
 // Per-instance quantities of the batch epilogue, from the reduced statistics.
 struct InstTerms {
   double nll, fg, f, s, cb;  // sum-nll, predicted-foreground count, fixed weight, sigmoid, c_b
 };
 __device__ __forceinline__ InstTerms inst_terms(const LossParams& p, int64_t b) {
   InstTerms t;
-  const double* st = p.inst_stats + b * p.C * kStatsPerClass;
+  const int64_t st = b * p.C * kStatsPerClass;
   t.nll = 0.0, t.fg = 0.0;
   for (int c = 0; c < p.C; ++c) {
-    t.nll += __ldcg(st + c * kStatsPerClass + DS_STAT_NLL);
-    if (c > 0) t.fg += __ldcg(st + c * kStatsPerClass + DS_STAT_PRED);
+    t.nll += load_stat(p, st + c * kStatsPerClass + DS_STAT_NLL);
+    if (c > 0) t.fg += load_stat(p, st + c * kStatsPerClass + DS_STAT_PRED);
   }
   const double V = (double)p.V;
   t.f = p.fixed_w ? (double)__ldg(p.fixed_w + b) : 1.0;
@@ -156,11 +181,11 @@ __device__ __forceinline__ void write_inst(const LossParams& p, int64_t b, const
   }
 }
 __device__ __forceinline__ void ce_terms(const LossParams& p, int64_t b, double& num, double& den) {
-  const double* st = p.inst_stats + b * p.C * kStatsPerClass;
+  const int64_t st = b * p.C * kStatsPerClass;
   for (int c = 0; c < p.C; ++c) {
     const double cw = (double)__ldg(p.class_w + c);
-    num += cw * __ldcg(st + c * kStatsPerClass + DS_STAT_NLL);
-    den += cw * __ldcg(st + c * kStatsPerClass + DS_STAT_LABEL);
+    num += cw * load_stat(p, st + c * kStatsPerClass + DS_STAT_NLL);
+    den += cw * load_stat(p, st + c * kStatsPerClass + DS_STAT_LABEL);
   }
 }
 __device__ __forceinline__ void write_losses(const LossParams& p, double L, double num, double den) {
@@ -272,9 +297,9 @@ __device__ __forceinline__ void flush_final(const LossParams& p, int cur_b, long
   for (int c = 0; c < CC; ++c) {
     if (c < p.C) {
       const long long v0 = warp_sum_ll(nll_fix[c]);
-      const long long v1 = warp_sum_ll((long long)lab_c[c]);
-      const long long v2 = warp_sum_ll((long long)pred_c[c]);
-      const long long v3 = warp_sum_ll((long long)tp_c[c]);
+      const long long v1 = (unsigned)warp_sum(lab_c[c]);  // a warp's counts fit 32 bits comfortably
+      const long long v2 = (unsigned)warp_sum(pred_c[c]);
+      const long long v3 = (unsigned)warp_sum(tp_c[c]);
       if (lane == 0) {
         s_acc[warp][c * 4 + DS_STAT_NLL] = v0, s_acc[warp][c * 4 + DS_STAT_LABEL] = v1;
         s_acc[warp][c * 4 + DS_STAT_PRED] = v2, s_acc[warp][c * 4 + DS_STAT_TP] = v3;
@@ -297,17 +322,26 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned n1 = gridDim.x < (unsigned)kTickets1 ? gridDim.x : (unsigned)kTickets1;
-    const unsigned i1 = blockIdx.x % n1;
-    const unsigned expect1 = gridDim.x / n1 + (i1 < gridDim.x % n1 ? 1u : 0u);
-    unsigned int* t1 = p.counters + (1 + i1) * kTicketStride;
     int last = 0;
-    if (atomicAdd(t1, 1u) == expect1 - 1) {
-      *t1 = 0u;  // leave the workspace clean for the next launch
-      __threadfence();
-      if (atomicAdd(p.counters, 1u) == n1 - 1) {
+    if (gridDim.x <= (unsigned)kSingleTicketGrid) {
+      // one persistent wave: arrivals are spread over the CTAs' finish times, one counter is enough and
+      // saves the last CTA a fence + a second atomic round trip (~1.4 us of pure tail)
+      if (atomicAdd(p.counters, 1u) == gridDim.x - 1) {
         *p.counters = 0u;
         last = 1;
+      }
+    } else {
+      const unsigned n1 = (unsigned)kTickets1;
+      const unsigned i1 = blockIdx.x % n1;
+      const unsigned expect1 = gridDim.x / n1 + (i1 < gridDim.x % n1 ? 1u : 0u);
+      unsigned int* t1 = p.counters + (1 + i1) * kTicketStride;
+      if (atomicAdd(t1, 1u) == expect1 - 1) {
+        *t1 = 0u;  // leave the workspace clean for the next launch
+        __threadfence();
+        if (atomicAdd(p.counters, 1u) == n1 - 1) {
+          *p.counters = 0u;
+          last = 1;
+        }
       }
     }
     s_last = last;
@@ -318,15 +352,22 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   const int S = p.C * kStatsPerClass;
   const double inv_scale = 1.0 / p.nll_scale;
   if (p.peer_bases == nullptr) {
+    __shared__ double s_stats[kSmemStats];
+    const bool staged = p.finalize && p.B_local == p.B_total && p.B_total * S <= kSmemStats;
     for (int64_t i = threadIdx.x; i < p.B_local * S; i += kThreads) {
       const long long v = (long long)__ldcg(p.acc + i);
       __stcg(p.acc + i, 0ull);
       const double d = ((i % kStatsPerClass) == DS_STAT_NLL) ? (double)v * inv_scale : (double)v;
       __stcg(p.inst_stats + p.b_offset * S + i, d);
+      if (staged) s_stats[i] = d;
     }
-    __threadfence();
+    if (!staged) __threadfence();
     __syncthreads();
-    if (p.finalize) finalize_block(p, scratch);
+    if (p.finalize) {
+      LossParams q = p;
+      q.stats_smem = staged ? s_stats : nullptr;
+      finalize_block(q, scratch);
+    }
     return;
   }
   // ---- fused exchange over NVLink peer memory (data-parallel loss) --------------------------------
@@ -414,7 +455,6 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
   constexpr int CC = C == 0 ? DS_MAX_CLASSES : C;
   const int nc = C == 0 ? p.C : C;
   __shared__ double s_scratch[kWarps + 1];
-  __shared__ double s_mean;  // mean sigmoid of the batch's data parameters (:744)
 
   const int lane = threadIdx.x & 31;
   const int64_t V = p.V;
@@ -425,13 +465,10 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
   float coef[CC];
 #pragma unroll
   for (int c = 0; c < CC; ++c) coef[c] = 0.f;
+  float mean_s = 1.f;
   if (GRAD) {
     if (p.mode == kModeDP) {
-      double ssum = 0.0;
-      for (int64_t i = threadIdx.x; i < p.B_total; i += kThreads) ssum += sigmoid_d(__ldg(p.bare_weight + i));
-      ssum = block_sum(ssum, s_scratch);
-      if (threadIdx.x == 0) s_mean = ssum / (double)p.B_total;
-      __syncthreads();
+      mean_s = batch_mean_sigmoid(p, s_scratch);
     } else if (p.mode == kModeCE) {
       double den = 0.0;
       for (int c = 0; c < nc; ++c) den += (double)__ldg(p.class_w + c) * __ldg(p.class_counts + c);
@@ -441,12 +478,13 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     }
   }
   // coefficient g * w_b / V of instance b (kModeDP / kModeBwd), recomputed when a warp changes instance
+  const float gV = (float)g / (float)V;
   auto instance_coef = [&](int b) -> float {
     if (!GRAD || p.mode == kModeCE) return 0.f;
-    if (p.mode == kModeBwd) return (float)(g * (double)__ldg(p.bare_weight + b * p.weight_stride) / (double)V);
+    if (p.mode == kModeBwd) return gV * __ldg(p.bare_weight + b * p.weight_stride);
     const int64_t bg = p.b_offset + b;
-    const double f = p.fixed_w ? (double)__ldg(p.fixed_w + bg) : 1.0;
-    return (float)(g * sigmoid_d(__ldg(p.bare_weight + bg)) / (s_mean * f) / (double)V);
+    const float f = p.fixed_w ? __ldg(p.fixed_w + bg) : 1.0f;
+    return gV * sigmoid_f(__ldg(p.bare_weight + bg)) / (mean_s * f);
   };
 
   // C == 2 without a separate Dice target: all label / true-positive counts come from one packed

@@ -99,7 +99,6 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   extern __shared__ __align__(128) unsigned char s_ring[];  // kTmaStages x kStageBytes
   __shared__ __align__(8) uint64_t s_full[kTmaStages], s_empty[kTmaStages];
   __shared__ double s_scratch[kWarps + 1];
-  __shared__ double s_mean;
 
   const int lane = threadIdx.x & 31;
   const int64_t V = p.V;
@@ -113,14 +112,12 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   }
 
   float coef[CC];
+  float mean_s = 1.f;
 #pragma unroll
   for (int c = 0; c < CC; ++c) coef[c] = 0.f;
   if (GRAD) {
     if (p.mode == kModeDP) {
-      double ssum = 0.0;
-      for (int64_t i = threadIdx.x; i < p.B_total; i += kThreads) ssum += sigmoid_d(__ldg(p.bare_weight + i));
-      ssum = block_sum(ssum, s_scratch);
-      if (threadIdx.x == 0) s_mean = ssum / (double)p.B_total;
+      mean_s = batch_mean_sigmoid(p, s_scratch);
     } else if (p.mode == kModeCE) {
       double den = 0.0;
       for (int c = 0; c < nc; ++c) den += (double)__ldg(p.class_w + c) * __ldg(p.class_counts + c);
@@ -128,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
       for (int c = 0; c < CC; ++c) coef[c] = (float)(g * (double)__ldg(p.class_w + c) / den);
     }
   }
-  __syncthreads();  // barriers initialised, s_mean published
+  __syncthreads();  // barriers initialised
 
   // this CTA's instance and its tiles: j, j + G, j + 2G, ...
   const int per_group = (int)gridDim.x / p.groups;
@@ -139,12 +136,13 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
 
   float coef0 = 0.f;
   if (GRAD && p.mode != kModeCE) {
+    const float gV = (float)g / (float)V;
     if (p.mode == kModeBwd) {
-      coef0 = (float)(g * (double)__ldg(p.bare_weight + b * p.weight_stride) / (double)V);
+      coef0 = gV * __ldg(p.bare_weight + b * p.weight_stride);
     } else {
       const int64_t bg = p.b_offset + b;
-      const double f = p.fixed_w ? (double)__ldg(p.fixed_w + bg) : 1.0;
-      coef0 = (float)(g * sigmoid_d(__ldg(p.bare_weight + bg)) / (s_mean * f) / (double)V);
+      const float f = p.fixed_w ? __ldg(p.fixed_w + bg) : 1.0f;
+      coef0 = gV * sigmoid_f(__ldg(p.bare_weight + bg)) / (mean_s * f);
     }
   }
 

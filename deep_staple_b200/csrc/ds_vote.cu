@@ -359,11 +359,22 @@ int launch_vote(const VoteParams& p0, cudaStream_t stream) {
   VoteParams p = p0;
   constexpr int VPT = VoteIn<LT, VECP>::VPT;
   p.units = p.V / VPT;
-  // grid: T targets x chunks, about `waves` full waves of resident CTAs, at least one iteration each
+  // grid: T targets x chunks.  Many small CTAs keep the memory front narrow (best for long candidate lists:
+  // 16 waves measured 6.8 TB/s vs 6.5 TB/s for 4), but every CTA pays the softmax prologue, so a CTA should
+  // own at least ~256 / (N * VPT) steps (a step costs N * VPT voxel-candidates per thread) -- unless that
+  // would leave SMs without a CTA (few targets): then one wave.
   const int sms = sm_count();
   const int per_sm = env_int("DS_VOTE_CTAS_PER_SM", 4), waves = env_int("DS_VOTE_WAVES", 16);
-  int64_t want = ((int64_t)sms * per_sm * waves + p.T - 1) / p.T;
   const int64_t max_chunks = (p.units + kThreads - 1) / kThreads;
+  int64_t want = ((int64_t)sms * per_sm * waves + p.T - 1) / p.T;
+  if (!env_int("DS_VOTE_RAW_GEOMETRY", 0)) {
+    const double per_step = (double)p.N * VPT;
+    const double iters = 256.0 / per_step > 1.0 ? 256.0 / per_step : 1.0;
+    int64_t by_iters = (int64_t)((double)p.units / (kThreads * iters));
+    const int64_t one_wave = ((int64_t)sms * per_sm + p.T - 1) / p.T;
+    if (by_iters < one_wave) by_iters = one_wave;
+    if (want > by_iters) want = by_iters;
+  }
   if (want > max_chunks) want = max_chunks;
   if (want < 1) want = 1;
   if (p.T * want > 0x7fffffffLL) return fail(DS_ERR_SHAPE, "ds_consensus_vote: T*chunks exceeds the grid limit");
