@@ -16,6 +16,12 @@ namespace {
 bool aligned16(const void* p) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
 size_t header_bytes() { return sizeof(unsigned int) * kWsCounters; }
+// exact integer statistics, padded to a multiple of 128 bytes so that the claim counters behind them start on a line
+size_t acc_bytes(int64_t B_local, int64_t C) {
+  const size_t n = sizeof(unsigned long long) * (size_t)B_local * (size_t)C * kStatsPerClass;
+  return (n + 127) / 128 * 128;
+}
+size_t claim_bytes(int64_t B_local) { return sizeof(unsigned int) * kTicketStride * kWarps * (size_t)B_local; }
 
 // Launch geometry of the persistent kernels: warp steps of 32 units; DS_LOSS_CTAS_PER_SM resident CTAs per SM (never more CTAs than there are
 // groups of kWarps tiles); fixed-point scale of the loss sums sized so that V voxels x 2^10 cannot
@@ -48,6 +54,17 @@ int setup_tiles(LossParams& p, const char* who, bool stats) {
   const int forced = env_int("DS_LOSS_GROUPS", 0);  // tuning experiments only
   if (forced > 0 && forced <= p.grid && p.grid % forced == 0) groups = forced;
   p.groups = groups;
+  // dynamic tail (LDG shell, one group per instance): the first ~80 % of an instance's steps stay static
+  // (a whole number of rounds of the group's warps), the rest is claimed step by step -- see loss_kernel.
+  // Needs enough steps per warp to be worth it; DS_LOSS_STATIC_PCT=100 switches it off.
+  if (p.claims) {
+    const int pct = env_int("DS_LOSS_STATIC_PCT", 80);
+    const int64_t warps_per_group = (int64_t)(p.grid / groups) * kWarps;
+    const int64_t rounds = p.steps_per_inst / warps_per_group;
+    const bool ok = stats && groups == p.B_local && !p.use_tma && pct < 100 && rounds >= 6 && p.V < 0x70000000LL;
+    if (ok) p.dyn_static = (unsigned)((rounds * pct / 100) * warps_per_group);
+    else p.claims = nullptr;
+  }
   int bits_v = 0;
   while (((int64_t)1 << bits_v) < p.V) ++bits_v;
   int e = 62 - bits_v - 10;
@@ -98,6 +115,7 @@ int carve_workspace(LossParams& p, void* workspace, size_t workspace_bytes, cons
     return fail(DS_ERR_WORKSPACE, "%s: workspace has %zu bytes, %zu needed", who, workspace_bytes, need);
   p.counters = reinterpret_cast<unsigned int*>(workspace);
   p.acc = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + header_bytes());
+  p.claims = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + header_bytes() + acc_bytes(p.B_local, p.C));
   return 0;
 }
 
@@ -115,7 +133,8 @@ int check_common(const char* who, const void* logits, int logit_dtype, const voi
 
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const LossParams p) {
   __shared__ double s_scratch[kWarps + 1];
-  finalize_block(p, s_scratch);
+  __shared__ EpiShared s_epi;
+  finalize_block(p, s_scratch, &s_epi, false);
 }
 
 template <typename T>
@@ -185,7 +204,7 @@ using namespace ds;
 
 extern "C" size_t ds_dp_loss_workspace_bytes(int64_t B_local, int64_t C) {
   if (B_local <= 0 || C <= 0) return 0;
-  return header_bytes() + sizeof(unsigned long long) * (size_t)B_local * (size_t)C * kStatsPerClass;
+  return header_bytes() + acc_bytes(B_local, C) + claim_bytes(B_local);
 }
 
 namespace {
@@ -342,6 +361,7 @@ extern "C" int ds_label_stats(const void* pred, int pred_dtype, const void* targ
   p.logits = pred, p.target = target, p.inst_stats = inst_stats;
   p.B_local = B, p.B_total = B, p.V = V, p.C = (int)C, p.mode = kModeNone, p.finalize = 0;
   if (int rc = carve_workspace(p, workspace, workspace_bytes, who)) return rc;
+  p.claims = nullptr;  // the label-statistics kernel is scheduled statically
   const int W = pred_dtype == DS_I64 ? 4 : 8;
   const bool vec = (V % W == 0) && aligned16(pred) && aligned16(target) && !env_int("DS_FORCE_SCALAR", 0);
   p.units = vec ? V / W : V;

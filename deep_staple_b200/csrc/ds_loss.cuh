@@ -67,6 +67,8 @@ struct LossParams {
   float* per_inst_out;          // [B_total, 4]
   unsigned int* counters;       // workspace header (kWsCounters words, zero between launches)
   unsigned long long* acc;      // workspace: [B_local, C, 4] exact integer statistics (zero between launches)
+  unsigned int* claims;         // workspace: [B_local, kWarps] step-claim counters, 128 B apart (zero between launches); null = static
+  unsigned dyn_static;          // warp steps of an instance that are scheduled statically (multiple of the group's warp count)
   int64_t B_local, B_total, b_offset, V;
   int64_t units;                // V / VEC
   int64_t steps_per_inst, n_steps;  // warp steps (32 units each) per instance / in total
@@ -80,6 +82,27 @@ struct LossParams {
   unsigned long long epoch;              // step counter, identical on all ranks, starts at 1
   int rank, world;
 };
+
+// Tuning builds only (-DDS_TIMING, never the shipped library): per-CTA %globaltimer stamps of the kernel
+// phases, read back with ds_debug_read (ds_loss_f32.cu) by tools/phase_times.py.
+#ifdef DS_TIMING
+static __device__ unsigned long long g_dbg[2048][10];
+__device__ __forceinline__ void dbg_stamp(int slot) {
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_dbg[blockIdx.x][slot] = t;
+    if (slot == 0) {
+      unsigned sm;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      g_dbg[blockIdx.x][8] = sm;
+    }
+  }
+}
+#define DS_STAMP(slot) dbg_stamp(slot)
+#else
+#define DS_STAMP(slot)
+#endif
 
 // sigmoid of a data parameter (:743): fp32 like the reference, widened for the batch sums
 __device__ __forceinline__ double sigmoid_d(float x) { return (double)(1.0f / (1.0f + expf(-x))); }
@@ -194,6 +217,87 @@ __device__ __forceinline__ void write_losses(const LossParams& p, double L, doub
   p.loss_out[1] = !p.class_w ? 0.f : (den != 0.0 ? (float)(num / den) : __int_as_float(0x7fc00000));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-phase batch epilogue for batches of <= kThreads instances (every configuration of the reference).
+// The finishing CTA sits on the kernel's critical path, so everything that does not depend on the
+// voxel statistics is computed BEFORE they are complete:
+//   fill  (kernel prologue, overlaps the first loads): sigmoid(p_b), f_b, class weights -> shared memory
+//   pre   (while the arrival ticket is in flight):     m = mean(s), 1/m, 1/f_b, 1/V, g  (all the divisions)
+//   post  (statistics complete):                       a handful of multiplies, one block reduction, stores
+// Same formulas as Appendix A of SURVEY.md; reciprocals replace divisions (<= 1 ulp in fp64 each).
+// ---------------------------------------------------------------------------------------------
+struct EpiShared {
+  float s[kThreads];            // sigmoid(p_b) in fp32 like the reference (:743)
+  float f[kThreads];            // fixed weighting f_b, 1 without (:747-748)
+  float cw[DS_MAX_CLASSES];     // class weights of the CE value (:716), 0 without
+  double red[3][kWarps];        // block reduction scratch of epi_post
+};
+struct EpiPre {
+  double s, inv_f, inv_m, inv_V, g;
+};
+__device__ __forceinline__ bool epi_two_phase(const LossParams& p) { return p.B_total <= kThreads; }
+__device__ __forceinline__ void epi_fill(const LossParams& p, EpiShared& e) {
+  const int i = threadIdx.x;
+  if (i < (int)p.B_total) {
+    e.s[i] = p.dp_outputs ? sigmoid_f(__ldg(p.bare_weight + i)) : 1.f;
+    e.f[i] = (p.dp_outputs && p.fixed_w) ? __ldg(p.fixed_w + i) : 1.f;
+  }
+  if (i < p.C) e.cw[i] = p.class_w ? __ldg(p.class_w + i) : 0.f;
+}
+// every warp sums the whole batch on its own (<= 8 values per lane + shuffles): no block barrier
+__device__ __forceinline__ EpiPre epi_pre(const LossParams& p, const EpiShared& e) {
+  EpiPre r;
+  const int B = (int)p.B_total, lane = threadIdx.x & 31, i = threadIdx.x;
+  double part = 0.0;
+  for (int k = lane; k < B; k += 32) part += (double)e.s[k];
+  r.inv_m = (double)B / warp_sum(part);  // 1 / mean(s)   (:744)
+  r.s = i < B ? (double)e.s[i] : 0.0;
+  r.inv_f = i < B ? 1.0 / (double)e.f[i] : 0.0;
+  r.inv_V = 1.0 / (double)p.V;
+  r.g = p.grad_scale ? (double)__ldcg(p.grad_scale) : 1.0;
+  return r;
+}
+__device__ __forceinline__ void epi_post(const LossParams& p, EpiShared& e, const EpiPre& pre) {
+  const int B = (int)p.B_total, i = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (B <= 32 && warp > 0) return;
+  const bool on = i < B;
+  double nll = 0.0, fg = 0.0, num = 0.0, den = 0.0;
+  if (on) {
+    const int64_t st = (int64_t)i * p.C * kStatsPerClass;
+    for (int c = 0; c < p.C; ++c) {
+      const double n_c = load_stat(p, st + c * kStatsPerClass + DS_STAT_NLL);
+      const double cw = (double)e.cw[c];
+      nll += n_c, num += cw * n_c;
+      den += cw * load_stat(p, st + c * kStatsPerClass + DS_STAT_LABEL);
+      if (c > 0) fg += load_stat(p, st + c * kStatsPerClass + DS_STAT_PRED);
+    }
+  }
+  const double cb = (nll - (p.use_risk ? fg : 0.0)) * pre.inv_V * pre.inv_f;  // (l_b - n_b / V) / f_b
+  double acc = warp_sum(on ? pre.s * cb : 0.0);
+  num = warp_sum(num), den = warp_sum(den);
+  if (B > 32) {
+    if (lane == 0) e.red[0][warp] = acc, e.red[1][warp] = num, e.red[2][warp] = den;
+    __syncthreads();
+    acc = num = den = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) acc += e.red[0][w], num += e.red[1][w], den += e.red[2][w];
+  }
+  const double L = p.dp_outputs ? acc * pre.inv_m : 0.0;  // :757 / :759
+  if (on && p.dp_outputs) {
+    // B == 1: weight / weight.mean() == 1 identically, the data parameter gets no gradient
+    const double grad = (B == 1) ? 0.0 : pre.g * pre.s * (1.0 - pre.s) * (cb - L / (double)B) * pre.inv_m;
+    if (p.d_bare_weight) p.d_bare_weight[i] = (float)grad;
+    if (p.per_inst_out) {
+      float* o = p.per_inst_out + (int64_t)i * DS_INST;
+      o[DS_INST_CE] = (float)(nll * pre.inv_V);
+      o[DS_INST_FG] = (float)fg;
+      o[DS_INST_WEIGHT] = (float)(pre.s * pre.inv_m * pre.inv_f);
+      o[DS_INST_SIGMOID] = (float)pre.s;
+    }
+  }
+  if (i == 0) write_losses(p, L, num, den);
+}
+
 // Batch epilogue on reduced statistics.  Called by all kThreads threads of one CTA; statistics are
 // read through L2 (other SMs just wrote them).
 //   s = sigmoid(p); m = mean(s); w = s / (m f)                       main_deep_staple.py:743-748
@@ -202,8 +306,18 @@ __device__ __forceinline__ void write_losses(const LossParams& p, double L, doub
 //   ce = sum_c cw_c S_c / sum_c cw_c N_c                               :716
 // Batches of <= 32 instances (every configuration of the reference) are finished by ONE warp with
 // shuffles only; larger batches use the whole CTA.
-__device__ __forceinline__ void finalize_block(const LossParams& p, double* scratch) {
+__device__ __forceinline__ void finalize_block(const LossParams& p, double* scratch, EpiShared* epi = nullptr,
+                                               bool epi_filled = false) {
   const int64_t B = p.B_total;
+  if (epi && epi_two_phase(p)) {
+    if (!epi_filled) {
+      epi_fill(p, *epi);
+      __syncthreads();
+    }
+    const EpiPre pre = epi_pre(p, *epi);
+    epi_post(p, *epi, pre);
+    return;
+  }
   const double g = p.grad_scale ? (double)__ldcg(p.grad_scale) : 1.0;
   if (B <= 32) {
     if (threadIdx.x >= 32) return;
@@ -317,16 +431,25 @@ __device__ __forceinline__ void flush_final(const LossParams& p, int cur_b, long
 
 // Kernel tail: the last CTA to finish turns the integer statistics into the [B, C, 4] doubles of
 // the ABI, zeroes the workspace for the next launch and (single-GPU) runs the batch epilogue.
-__device__ __forceinline__ void finish_launch(const LossParams& p, double* scratch) {
+__device__ __forceinline__ void finish_launch(const LossParams& p, double* scratch, EpiShared* epi = nullptr) {
   __shared__ int s_last;
+  // `epi` was filled in the kernel prologue (epi_fill) iff the launch finalizes a batch of <= kThreads
+  const bool two_phase = epi && p.finalize && epi_two_phase(p);
+  EpiPre pre{};
   __threadfence();
   __syncthreads();
+  DS_STAMP(5);
+  const bool single = gridDim.x <= (unsigned)kSingleTicketGrid;
+  unsigned ticket = 0u;
+  // one persistent wave: arrivals are spread over the CTAs' finish times, one counter is enough and
+  // saves the last CTA a fence + a second atomic round trip (~1.4 us of pure tail)
+  if (single && threadIdx.x == 0) ticket = atomicAdd(p.counters, 1u);
+  // the statistics-independent half of the epilogue (all its divisions) runs while the ticket is in flight
+  if (two_phase) pre = epi_pre(p, *epi);
   if (threadIdx.x == 0) {
     int last = 0;
-    if (gridDim.x <= (unsigned)kSingleTicketGrid) {
-      // one persistent wave: arrivals are spread over the CTAs' finish times, one counter is enough and
-      // saves the last CTA a fence + a second atomic round trip (~1.4 us of pure tail)
-      if (atomicAdd(p.counters, 1u) == gridDim.x - 1) {
+    if (single) {
+      if (ticket == gridDim.x - 1) {
         *p.counters = 0u;
         last = 1;
       }
@@ -347,8 +470,11 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
     s_last = last;
   }
   __syncthreads();
+  DS_STAMP(6);
   if (!s_last) return;
   __threadfence();
+  if (p.claims)  // every CTA has stopped claiming: leave the counters clean for the next launch
+    for (int i = threadIdx.x; i < (int)p.B_local * kWarps; i += kThreads) p.claims[(size_t)i * kTicketStride] = 0u;
   const int S = p.C * kStatsPerClass;
   const double inv_scale = 1.0 / p.nll_scale;
   if (p.peer_bases == nullptr) {
@@ -366,8 +492,11 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
     if (p.finalize) {
       LossParams q = p;
       q.stats_smem = staged ? s_stats : nullptr;
-      finalize_block(q, scratch);
+      if (two_phase) epi_post(q, *epi, pre);
+      else finalize_block(q, scratch);
     }
+    __syncthreads();
+    DS_STAMP(7);
     return;
   }
   // ---- fused exchange over NVLink peer memory (data-parallel loss) --------------------------------
@@ -420,7 +549,8 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   full.inst_stats = slot_of(__ldg(p.peer_bases + p.rank));
   if (p.inst_stats)
     for (int64_t i = threadIdx.x; i < n_all; i += kThreads) p.inst_stats[i] = __ldcg(full.inst_stats + i);
-  finalize_block(full, scratch);
+  if (two_phase) epi_post(full, *epi, pre);
+  else finalize_block(full, scratch);
   if (s_timeout && threadIdx.x == 0 && p.loss_out) p.loss_out[0] = p.loss_out[1] = __int_as_float(0x7fc00000);
 }
 
@@ -455,10 +585,43 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
   constexpr int CC = C == 0 ? DS_MAX_CLASSES : C;
   const int nc = C == 0 ? p.C : C;
   __shared__ double s_scratch[kWarps + 1];
+  __shared__ EpiShared s_epi;
+  DS_STAMP(0);
 
   const int lane = threadIdx.x & 31;
   const int64_t V = p.V;
   const bool uniform_coef = p.mode != kModeCE;
+
+  // Launch ramp (forward-only launches): the prologue below (data-parameter loads, sigmoids, divisions)
+  // leaves DRAM idle for ~2 us -- ask L2 for this warp's first two steps before anything else.  Measured:
+  // -0.5 us without gradients, but +2 us with them (back-to-back launches), hence the GRAD switch.
+#ifndef DS_NO_PREFETCH
+  if (!GRAD && p.groups == p.B_local && V < 0x70000000LL) {
+    const int per_group = (int)gridDim.x / p.groups;
+    const int b = (int)blockIdx.x / per_group;
+    const unsigned wg = (unsigned)((int)blockIdx.x - b * per_group) * kWarps + (threadIdx.x >> 5);
+    const unsigned stride = (unsigned)per_group * kWarps;
+    const LT* zb = reinterpret_cast<const LT*>(p.logits) + (int64_t)b * nc * V;
+    const TT* tb = reinterpret_cast<const TT*>(p.target) + (int64_t)b * V;
+#ifndef DS_PREFETCH_STEPS
+#define DS_PREFETCH_STEPS 2
+#endif
+#pragma unroll
+    for (int k = 0; k < DS_PREFETCH_STEPS; ++k) {
+      const unsigned s = wg + (unsigned)k * stride;
+      const int64_t off = ((int64_t)s * 32 + lane) * VEC;
+      if (s < (unsigned)p.steps_per_inst && off < V) {
+        if ((lane * VEC * (int)sizeof(LT)) % 128 == 0)
+          for (int c = 0; c < nc; ++c) prefetch_l2(zb + (int64_t)c * V + off);
+        if ((lane * VEC * (int)sizeof(TT)) % 128 == 0) prefetch_l2(tb + off);
+        if constexpr (STATS && DICE)
+          if ((lane * VEC * (int)sizeof(TT)) % 128 == 0)
+            prefetch_l2(reinterpret_cast<const TT*>(p.dice_target) + (int64_t)b * V + off);
+      }
+    }
+  }
+#endif
+  if (STATS && p.finalize && epi_two_phase(p)) epi_fill(p, s_epi);
   const double g = (GRAD && p.grad_scale) ? (double)__ldg(p.grad_scale) : 1.0;
 
   // gradient coefficients that do not depend on the instance
@@ -607,8 +770,42 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
       cur_b = b;
       coef0 = instance_coef(b);
     }
-    for (unsigned s = wg; s < n_steps; s += stride, off += dv)
+    DS_STAMP(1);
+    // static part: warp w takes steps w, w + W, ... -- all of them, or (dynamic tail) the first dyn_static
+    const unsigned n_sched = p.claims ? p.dyn_static : n_steps;
+#ifdef DS_TIMING
+    if (wg < n_sched && off < n_vox) process(zb, tb, db, gb, off);
+    DS_STAMP(2);
+    for (unsigned s = wg + stride; s < n_sched; s += stride) {
+      off += dv;
       if (off < n_vox) process(zb, tb, db, gb, off);
+    }
+#else
+    for (unsigned s = wg; s < n_sched; s += stride, off += dv)
+      if (off < n_vox) process(zb, tb, db, gb, off);
+#endif
+    // Dynamic tail.  Equal static shares do not finish together: under a saturated memory system the CTAs of
+    // one SM drift ~4 us apart and SMs ~7 us (measured), and the kernel ends with its slowest warp.  The
+    // last ~20 % of an instance's steps are therefore claimed one at a time from kWarps counters per
+    // instance (warp w of every CTA of the group shares counter w: ~75 warps from as many SMs, <= 50
+    // same-address atomics per us), still in address order, so the front stays narrow.  The claim for the
+    // next step is in flight while the current one is processed.
+    if (p.claims) {
+      cur_b = b;
+      if (wg >= n_steps) coef0 = instance_coef(b);
+      const unsigned sub = threadIdx.x >> 5;
+      unsigned int* ctr = p.claims + ((size_t)b * kWarps + sub) * kTicketStride;
+      unsigned pending = 0u;
+      if (lane == 0) pending = atomicAdd(ctr, 1u);
+      while (true) {
+        const unsigned s = n_sched + sub + (unsigned)kWarps * __shfl_sync(0xffffffffu, pending, 0);
+        if (s >= n_steps) break;
+        if (lane == 0) pending = atomicAdd(ctr, 1u);
+        const unsigned o = (s * 32u + lane) * VEC;
+        if (o < n_vox) process(zb, tb, db, gb, o);
+      }
+    }
+    DS_STAMP(3);
   } else {
     const StepWalk walk(p);
     int b = walk.b0;
@@ -636,7 +833,8 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     if constexpr (PACKED) empty_hist();
     merge_fast();
     flush_final<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c);
-    finish_launch(p, s_scratch);
+    DS_STAMP(4);
+    finish_launch(p, s_scratch, &s_epi);
   }
 }
 

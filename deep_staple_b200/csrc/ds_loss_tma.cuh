@@ -100,32 +100,11 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   __shared__ __align__(8) uint64_t s_full[kTmaStages], s_empty[kTmaStages];
   __shared__ double s_scratch[kWarps + 1];
 
+  __shared__ EpiShared s_epi;
+
   const int lane = threadIdx.x & 31;
   const int64_t V = p.V;
   const bool uniform_coef = p.mode != kModeCE;
-  const double g = (GRAD && p.grad_scale) ? (double)__ldg(p.grad_scale) : 1.0;
-
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], kWarps);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-
-  float coef[CC];
-  float mean_s = 1.f;
-#pragma unroll
-  for (int c = 0; c < CC; ++c) coef[c] = 0.f;
-  if (GRAD) {
-    if (p.mode == kModeDP) {
-      mean_s = batch_mean_sigmoid(p, s_scratch);
-    } else if (p.mode == kModeCE) {
-      double den = 0.0;
-      for (int c = 0; c < nc; ++c) den += (double)__ldg(p.class_w + c) * __ldg(p.class_counts + c);
-#pragma unroll
-      for (int c = 0; c < CC; ++c) coef[c] = (float)(g * (double)__ldg(p.class_w + c) / den);
-    }
-  }
-  __syncthreads();  // barriers initialised
 
   // this CTA's instance and its tiles: j, j + G, j + 2G, ...
   const int per_group = (int)gridDim.x / p.groups;
@@ -133,19 +112,6 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   const int j0 = (int)blockIdx.x - b * per_group;
   const int64_t n_tiles = (V + kTileV - 1) / kTileV;
   const int64_t my_tiles = j0 < n_tiles ? (n_tiles - j0 + per_group - 1) / per_group : 0;
-
-  float coef0 = 0.f;
-  if (GRAD && p.mode != kModeCE) {
-    const float gV = (float)g / (float)V;
-    if (p.mode == kModeBwd) {
-      coef0 = gV * __ldg(p.bare_weight + b * p.weight_stride);
-    } else {
-      const int64_t bg = p.b_offset + b;
-      const float f = p.fixed_w ? __ldg(p.fixed_w + bg) : 1.0f;
-      coef0 = gV * sigmoid_f(__ldg(p.bare_weight + bg)) / (mean_s * f);
-    }
-  }
-
   const LT* __restrict__ zb = reinterpret_cast<const LT*>(p.logits) + (int64_t)b * nc * V;
   LT* __restrict__ gb = reinterpret_cast<LT*>(p.dlogits) + (int64_t)b * nc * V;
   const TT* __restrict__ tb = reinterpret_cast<const TT*>(p.target) + (int64_t)b * V;
@@ -165,6 +131,47 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
     tma_load_1d(st + C * kPlaneBytes, tb + v0, (unsigned)(nv * sizeof(TT)), &s_full[s]);
   };
 
+  // Launch ramp: the first tiles go out before the prologue (data-parameter loads, sigmoids, divisions),
+  // which would otherwise leave DRAM idle for its ~1.5 us.
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], kWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int64_t pre = my_tiles < kTmaStages - 1 ? my_tiles : kTmaStages - 1;
+    for (int64_t k = 0; k < pre; ++k) produce(k);
+  }
+  if (p.finalize && epi_two_phase(p)) epi_fill(p, s_epi);
+
+  const double g = (GRAD && p.grad_scale) ? (double)__ldg(p.grad_scale) : 1.0;
+  float coef[CC];
+  float mean_s = 1.f;
+#pragma unroll
+  for (int c = 0; c < CC; ++c) coef[c] = 0.f;
+  if (GRAD) {
+    if (p.mode == kModeDP) {
+      mean_s = batch_mean_sigmoid(p, s_scratch);
+    } else if (p.mode == kModeCE) {
+      double den = 0.0;
+      for (int c = 0; c < nc; ++c) den += (double)__ldg(p.class_w + c) * __ldg(p.class_counts + c);
+#pragma unroll
+      for (int c = 0; c < CC; ++c) coef[c] = (float)(g * (double)__ldg(p.class_w + c) / den);
+    }
+  }
+  __syncthreads();  // barriers initialised
+
+  float coef0 = 0.f;
+  if (GRAD && p.mode != kModeCE) {
+    const float gV = (float)g / (float)V;
+    if (p.mode == kModeBwd) {
+      coef0 = gV * __ldg(p.bare_weight + b * p.weight_stride);
+    } else {
+      const int64_t bg = p.b_offset + b;
+      const float f = p.fixed_w ? __ldg(p.fixed_w + bg) : 1.0f;
+      coef0 = gV * sigmoid_f(__ldg(p.bare_weight + bg)) / (mean_s * f);
+    }
+  }
+
   constexpr bool PACKED = C == 2;
   constexpr int kHistSteps = 252 / VEC;
   long long nll_fix[CC];
@@ -180,11 +187,6 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
     lab_c[0] += h0 + h2, lab_c[1] += h1 + h3, tp_c[0] += h0, tp_c[1] += h3;
     hist = 0u, hist_steps = 0;
   };
-
-  if (threadIdx.x == 0) {
-    const int64_t pre = my_tiles < kTmaStages - 1 ? my_tiles : kTmaStages - 1;
-    for (int64_t k = 0; k < pre; ++k) produce(k);
-  }
 
   for (int64_t k = 0; k < my_tiles; ++k) {
     if (threadIdx.x == 0 && k + kTmaStages - 1 < my_tiles) produce(k + kTmaStages - 1);
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   tp_c[1] += n_both, tp_c[0] += seen_fast - n_t1 - n_am1 + n_both;
   pred_c[1] += n_am1, pred_c[0] += seen_fast - n_am1;
   flush_final<CC>(p, my_tiles > 0 ? b : -1, nll_fix, lab_c, pred_c, tp_c);
-  finish_launch(p, s_scratch);
+  finish_launch(p, s_scratch, &s_epi);
 }
 
 }  // namespace ds

@@ -108,7 +108,20 @@ def aten_cuda_case(name, B, C, S, ldt, steps=10):
           f"({B * V / sec / 1e9:7.1f} Gvox/s)  [stock torch CUDA composition]", flush=True)
 
 
+_FILTER = [f for f in os.environ.get("DS_CASES", "").split(",") if f]
+
+
+def _wrap(fn):
+    def run(name, *a, **k):
+        if _FILTER and not any(f in name for f in _FILTER):
+            return
+        fn(name, *a, **k)
+    return run
+
+
 if __name__ == "__main__":
+    # DS_CASES=substr[,substr...] runs only the matching cases
+    loss_case, vote_case, aten_cuda_case = _wrap(loss_case), _wrap(vote_case), _wrap(aten_cuda_case)
     S3 = (128, 128, 128)
     loss_case("cfg2 fp32/int64 fwd+bwd", 8, 2, S3, torch.float32, torch.int64)
     loss_case("cfg2 fp16/int64 fwd+bwd (AMP)", 8, 2, S3, torch.float16, torch.int64)
