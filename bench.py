@@ -216,7 +216,7 @@ def run_reference_arm(args):
     emit(line)
 
 
-def loss_config_dict(n_gpus, exchange="inside the loss kernel over NVLink peer memory"):
+def loss_config_dict(n_gpus, exchange="inside the loss kernel over NVLink peer memory", launch="n/a"):
     c = LOSS_CFG
     return {
         "workload": "dp-weighted CE loss fwd+bwd (risk regularisation, fixed weighting, class-weighted CE value, "
@@ -225,6 +225,7 @@ def loss_config_dict(n_gpus, exchange="inside the loss kernel over NVLink peer m
         "logits_dtype": "float32", "label_dtype": "int64", "grad_scale": c["grad_scale"],
         "parallelism": f"dp{n_gpus} (instances sharded; per-instance statistics exchanged {exchange})" if n_gpus > 1 else "single GPU",
         "l2": "inputs rotate over 3 buffer sets of 403 MB (> 126 MB L2); no reuse between steps",
+        "launch": launch,
     }
 
 
@@ -327,6 +328,55 @@ def timed(fn, steps, warmup, barrier=None):
     if barrier:
         barrier()
     return e0.elapsed_time(e1) / 1e3
+
+
+def graph_chunk(steps, cap=256):
+    """Steps per captured graph: `steps` itself when small, else its largest divisor <= cap (0: none useful)."""
+    if steps <= cap:
+        return steps
+    best = max(d for d in range(1, cap + 1) if steps % d == 0)
+    return best if best >= 16 else 0
+
+
+def timed_graph(step_obj, fn, steps, warmup, barrier=None):
+    """Like timed(), but the K steps are replayed from a CUDA graph (steps // chunk replays of a chunk-step
+    graph captured on a side stream): the launches are enqueued by the GPU front end instead of one by one
+    from Python, which removes ~2 us of inter-kernel gap per step.  Still exactly K steps between two CUDA
+    events on the replaying stream, after W warm-up steps.  Returns (seconds, launches_per_step)."""
+    import deep_staple_b200 as ds
+
+    chunk = graph_chunk(steps)
+    if chunk == 0:
+        return timed(fn, steps, warmup, barrier), None
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    main_stream = step_obj.stream
+    step_obj.stream = side.cuda_stream
+    try:
+        with torch.cuda.stream(side):
+            n0 = ds.launch_count()
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(chunk):
+                    fn()
+            per_step = (ds.launch_count() - n0) / chunk
+    finally:
+        step_obj.stream = main_stream
+    graph.replay()  # one untimed replay: graph upload
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps // chunk):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return e0.elapsed_time(e1) / 1e3, per_step
 
 
 def e2e_loss(device, steps, warmup):
@@ -453,6 +503,8 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-vote", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--launch", default="graph", choices=["graph", "stream"],
+                    help="timed steps replayed from a CUDA graph (default) or launched one by one from Python")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: statistics exchange inside the loss kernel over NVLink peer memory, or NCCL all-gather")
     args = ap.parse_args()
@@ -487,9 +539,15 @@ def main():
     sampler.start()
     for _ in range(args.warmup):
         step.step()
+    use_graph = args.launch == "graph" and (world == 1 or args.exchange == "fused")
     launches0 = ds.launch_count()
-    sec = timed(step.step, args.steps, 0, barrier)
-    launches = ds.launch_count() - launches0
+    if use_graph:
+        sec, per_step = timed_graph(step, step.step, args.steps, 0, barrier)
+        launches = round(per_step * args.steps) if per_step is not None else ds.launch_count() - launches0
+        use_graph = per_step is not None
+    else:
+        sec = timed(step.step, args.steps, 0, barrier)
+        launches = ds.launch_count() - launches0
     if dist:
         dist.barrier()  # nobody leaves the fused-exchange phase while a peer still waits on its flags
     if dist:
@@ -497,7 +555,10 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         sec = float(tmax.item())
     # the dominant kernel alone (no collective, no epilogue launch): average launch duration
-    ksec = timed(step.kernel, args.steps, max(3, args.warmup // 2))
+    if use_graph:
+        ksec, _ = timed_graph(step, step.kernel, args.steps, max(3, args.warmup // 2))
+    else:
+        ksec = timed(step.kernel, args.steps, max(3, args.warmup // 2))
     e2e = None
     if not args.skip_e2e:
         del step.sets[1:], step.dlogits[1:]
@@ -537,7 +598,9 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": loss_config_dict(world, "inside the loss kernel over NVLink peer memory" if args.exchange == "fused"
-                                       else "by NCCL all-gather + epilogue launch"),
+                                       else "by NCCL all-gather + epilogue launch",
+                                       f"CUDA graph of {graph_chunk(args.steps)} steps, replayed" if use_graph
+                                       else "one C-ABI call per step from the host"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_loss_fwdbwd_ncu_summary.txt",
                          "kernel": "ds::loss_kernel<float,int64,2,4,true,true>",

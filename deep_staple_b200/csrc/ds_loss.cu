@@ -61,9 +61,22 @@ int setup_tiles(LossParams& p, const char* who, bool stats) {
     const int pct = env_int("DS_LOSS_STATIC_PCT", 80);
     const int64_t warps_per_group = (int64_t)(p.grid / groups) * kWarps;
     const int64_t rounds = p.steps_per_inst / warps_per_group;
-    const bool ok = stats && groups == p.B_local && !p.use_tma && pct < 100 && rounds >= 6 && p.V < 0x70000000LL;
-    if (ok) p.dyn_static = (unsigned)((rounds * pct / 100) * warps_per_group);
-    else p.claims = nullptr;
+    if (p.use_tma) {
+      // TMA shell: tiles can be claimed per CTA by the producer thread (one counter per instance, see
+      // ds_loss_tma.cuh).  Off by default (DS_LOSS_TMA_STATIC_PCT=100): measured on cfg2 / cfg5 it is a wash at
+      // best (fp16 51.4 vs 52.4 us at 90 % static) and a loss elsewhere (uint8 labels 60.7 vs 58.6 us, C = 3
+      // 211.8 vs 210.1 us) -- two CTAs per SM drift less than four, and the claim sits on the producer's path.
+      const int64_t tiles = (p.units + kThreads - 1) / kThreads, tile_rounds = tiles / (p.grid / groups);
+      const int64_t k_static = tile_rounds * env_int("DS_LOSS_TMA_STATIC_PCT", 100) / 100;
+      if (groups == p.B_local && tile_rounds >= 6 && k_static >= kTmaStages - 1 && k_static < tile_rounds)
+        p.dyn_static = (unsigned)k_static;
+      else
+        p.claims = nullptr;
+    } else {
+      const bool ok = stats && groups == p.B_local && pct < 100 && rounds >= 6 && p.V < 0x70000000LL;
+      if (ok) p.dyn_static = (unsigned)((rounds * pct / 100) * warps_per_group);
+      else p.claims = nullptr;
+    }
   }
   int bits_v = 0;
   while (((int64_t)1 << bits_v) < p.V) ++bits_v;
@@ -93,7 +106,7 @@ int setup_geometry(LossParams& p, int logit_dtype, int target_dtype, bool* vec_o
   const int choice = env_int("DS_LOSS_TMA", -1);
   p.use_tma = eligible && (choice < 0 ? heavy : choice != 0);
   const int rc = setup_tiles(p, who, stats);
-  if (p.use_tma && p.groups != p.B_local) p.use_tma = 0;
+  if (p.use_tma && p.groups != p.B_local) p.use_tma = 0, p.claims = nullptr;
   return rc;
 }
 
@@ -224,7 +237,7 @@ int dp_loss_fwd_bwd_impl(const char* who, const void* logits, int logit_dtype, c
   if (B_total > DS_MAX_BATCH) return fail(DS_ERR_SHAPE, "%s: B_total=%lld exceeds %d", who, (long long)B_total, DS_MAX_BATCH);
   const bool whole = B_local == B_total;
   if ((whole || peer_bases) && !loss_out) return fail(DS_ERR_NULL, "%s: loss_out is required", who);
-  if (peer_bases && (world < 1 || world > kThreads || rank < 0 || rank >= world || epoch == 0))
+  if (peer_bases && (world < 1 || world > kThreads || rank < 0 || rank >= world))
     return fail(DS_ERR_ARG, "%s: bad rank/world/epoch %d/%d/%llu", who, rank, world, epoch);
   LossParams p{};
   p.logits = logits, p.target = target, p.dice_target = dice_target, p.dlogits = dlogits;
@@ -252,7 +265,7 @@ extern "C" int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const voi
 
 extern "C" size_t ds_dp_loss_exchange_bytes(int64_t B_total, int64_t C, int world) {
   if (B_total <= 0 || C <= 0 || world <= 0) return 0;
-  return sizeof(double) * 2 * (size_t)B_total * (size_t)C * kStatsPerClass + sizeof(unsigned long long) * (size_t)world;
+  return sizeof(double) * 2 * (size_t)B_total * (size_t)C * kStatsPerClass + sizeof(unsigned long long) * ((size_t)world + 1);
 }
 
 extern "C" int ds_dp_loss_fwd_bwd_exchange(const void* logits, int logit_dtype, const void* target, int target_dtype,

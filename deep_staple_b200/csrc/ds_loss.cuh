@@ -86,13 +86,14 @@ struct LossParams {
 // Tuning builds only (-DDS_TIMING, never the shipped library): per-CTA %globaltimer stamps of the kernel
 // phases, read back with ds_debug_read (ds_loss_f32.cu) by tools/phase_times.py.
 #ifdef DS_TIMING
-static __device__ unsigned long long g_dbg[2048][10];
+static __device__ unsigned long long g_dbg[2048][16];
 __device__ __forceinline__ void dbg_stamp(int slot) {
   if (threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_dbg[blockIdx.x][slot] = t;
     if (slot == 0) {
+      g_dbg[blockIdx.x][9] = 0;
       unsigned sm;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
       g_dbg[blockIdx.x][8] = sm;
@@ -233,7 +234,7 @@ struct EpiShared {
   double red[3][kWarps];        // block reduction scratch of epi_post
 };
 struct EpiPre {
-  double s, inv_f, inv_m, inv_V, g;
+  double s, inv_f, inv_m, inv_V, inv_B, g;
 };
 __device__ __forceinline__ bool epi_two_phase(const LossParams& p) { return p.B_total <= kThreads; }
 __device__ __forceinline__ void epi_fill(const LossParams& p, EpiShared& e) {
@@ -244,16 +245,67 @@ __device__ __forceinline__ void epi_fill(const LossParams& p, EpiShared& e) {
   }
   if (i < p.C) e.cw[i] = p.class_w ? __ldg(p.class_w + i) : 0.f;
 }
+// Prologue of the data-parameter mode.  One pass over the batch's data parameters per warp (one round of
+// loads, two sigmoids per lane, shuffles) yields the batch mean of the sigmoids (:744), the gradient
+// coefficient g w_b / V of the CTA's home instance and -- for the finishing CTA's epilogue -- the
+// per-instance sigmoids / fixed weights in shared memory.  It sits on the launch ramp (~150 dependent
+// instructions when mean, coefficient and epilogue inputs were computed one after the other).
+struct DpPrologue {
+  float mean_s, coef_home;
+  bool have_home;
+};
+__device__ __forceinline__ DpPrologue dp_prologue(const LossParams& p, EpiShared& e, bool grad, bool fill, int home,
+                                                  float gV, double* scratch) {
+  DpPrologue r{1.f, 0.f, false};
+  const int lane = threadIdx.x & 31, B = (int)p.B_total;
+  if (B <= 64) {
+    const bool on0 = lane < B, on1 = lane + 32 < B;
+    const float x0 = on0 ? __ldg(p.bare_weight + lane) : 0.f;
+    const float x1 = on1 ? __ldg(p.bare_weight + lane + 32) : 0.f;
+    const float f0 = (on0 && p.fixed_w) ? __ldg(p.fixed_w + lane) : 1.f;
+    const float f1 = (on1 && p.fixed_w) ? __ldg(p.fixed_w + lane + 32) : 1.f;
+    const float s0 = on0 ? sigmoid_f(x0) : 0.f, s1 = on1 ? sigmoid_f(x1) : 0.f;
+    r.mean_s = warp_sum(s0 + s1) / (float)B;
+    if (fill && threadIdx.x < 32) {
+      if (on0) e.s[lane] = s0, e.f[lane] = f0;
+      if (on1) e.s[lane + 32] = s1, e.f[lane + 32] = f1;
+    }
+    if (grad && home >= 0) {
+      const int bg = (int)p.b_offset + home;
+      const float sb = __shfl_sync(0xffffffffu, bg < 32 ? s0 : s1, bg & 31);
+      const float fb = __shfl_sync(0xffffffffu, bg < 32 ? f0 : f1, bg & 31);
+      r.coef_home = gV * sb / (r.mean_s * fb);
+      r.have_home = true;
+    }
+    if (fill && (int)threadIdx.x < p.C) e.cw[threadIdx.x] = p.class_w ? __ldg(p.class_w + threadIdx.x) : 0.f;
+  } else {
+    if (grad) r.mean_s = batch_mean_sigmoid(p, scratch);
+    if (fill) epi_fill(p, e);
+  }
+  return r;
+}
+
+// 1 / x for positive normal x inside the fp32 range: fp32 reciprocal + two Newton steps in fp64 (|rel err|
+// ~ 1e-16).  The epilogue runs once, on one CTA, on the kernel's critical path: a called fp64 division is
+// ~60 dependent instructions, this is 6.
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r = (double)__frcp_rn((float)x);
+  double err = fma(-x, r, 1.0);
+  r = fma(r, err, r);
+  err = fma(-x, r, 1.0);
+  return fma(r, err, r);
+}
 // every warp sums the whole batch on its own (<= 8 values per lane + shuffles): no block barrier
 __device__ __forceinline__ EpiPre epi_pre(const LossParams& p, const EpiShared& e) {
   EpiPre r;
   const int B = (int)p.B_total, lane = threadIdx.x & 31, i = threadIdx.x;
   double part = 0.0;
   for (int k = lane; k < B; k += 32) part += (double)e.s[k];
-  r.inv_m = (double)B / warp_sum(part);  // 1 / mean(s)   (:744)
+  r.inv_m = (double)B * rcp_fast(warp_sum(part));  // 1 / mean(s)   (:744)
   r.s = i < B ? (double)e.s[i] : 0.0;
-  r.inv_f = i < B ? 1.0 / (double)e.f[i] : 0.0;
-  r.inv_V = 1.0 / (double)p.V;
+  r.inv_f = i < B ? rcp_fast((double)e.f[i]) : 0.0;
+  r.inv_V = rcp_fast((double)p.V);
+  r.inv_B = rcp_fast((double)B);
   r.g = p.grad_scale ? (double)__ldcg(p.grad_scale) : 1.0;
   return r;
 }
@@ -285,7 +337,7 @@ __device__ __forceinline__ void epi_post(const LossParams& p, EpiShared& e, cons
   const double L = p.dp_outputs ? acc * pre.inv_m : 0.0;  // :757 / :759
   if (on && p.dp_outputs) {
     // B == 1: weight / weight.mean() == 1 identically, the data parameter gets no gradient
-    const double grad = (B == 1) ? 0.0 : pre.g * pre.s * (1.0 - pre.s) * (cb - L / (double)B) * pre.inv_m;
+    const double grad = (B == 1) ? 0.0 : pre.g * pre.s * (1.0 - pre.s) * (cb - L * pre.inv_B) * pre.inv_m;
     if (p.d_bare_weight) p.d_bare_weight[i] = (float)grad;
     if (p.per_inst_out) {
       float* o = p.per_inst_out + (int64_t)i * DS_INST;
@@ -295,7 +347,10 @@ __device__ __forceinline__ void epi_post(const LossParams& p, EpiShared& e, cons
       o[DS_INST_SIGMOID] = (float)pre.s;
     }
   }
-  if (i == 0) write_losses(p, L, num, den);
+  if (i == 0 && p.loss_out) {
+    p.loss_out[0] = (float)L;
+    p.loss_out[1] = !p.class_w ? 0.f : (den > 0.0 ? (float)(num * rcp_fast(den)) : __int_as_float(0x7fc00000));
+  }
 }
 
 // Batch epilogue on reduced statistics.  Called by all kThreads threads of one CTA; statistics are
@@ -446,6 +501,7 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   if (single && threadIdx.x == 0) ticket = atomicAdd(p.counters, 1u);
   // the statistics-independent half of the epilogue (all its divisions) runs while the ticket is in flight
   if (two_phase) pre = epi_pre(p, *epi);
+  DS_STAMP(10);
   if (threadIdx.x == 0) {
     int last = 0;
     if (single) {
@@ -473,6 +529,7 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   DS_STAMP(6);
   if (!s_last) return;
   __threadfence();
+  DS_STAMP(11);
   if (p.claims)  // every CTA has stopped claiming: leave the counters clean for the next launch
     for (int i = threadIdx.x; i < (int)p.B_local * kWarps; i += kThreads) p.claims[(size_t)i * kTicketStride] = 0u;
   const int S = p.C * kStatsPerClass;
@@ -489,6 +546,7 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
     }
     if (!staged) __threadfence();
     __syncthreads();
+    DS_STAMP(12);
     if (p.finalize) {
       LossParams q = p;
       q.stats_smem = staged ? s_stats : nullptr;
@@ -508,11 +566,15 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   // A peer can be at most one step ahead (it needs our flag of step k+1 to finish step k+1), so two
   // statistic slots are enough.
   const int64_t n_all = p.B_total * S;
-  auto slot_of = [&](unsigned long long base) -> double* {
-    return reinterpret_cast<double*>(base) + (p.epoch & 1ull) * n_all;
-  };
   auto flags_of = [&](unsigned long long base) -> unsigned long long* {
     return reinterpret_cast<unsigned long long*>(base) + 2 * n_all;
+  };
+  // step counter: the caller's (epoch > 0) or the one kept behind the flags of this rank's own buffer
+  // (epoch == 0), which makes the launch independent of host state -- CUDA-graph capturable
+  unsigned long long* my_step = flags_of(__ldg(p.peer_bases + p.rank)) + p.world;
+  const unsigned long long epoch = p.epoch ? p.epoch : __ldcg(my_step) + 1ull;
+  auto slot_of = [&](unsigned long long base) -> double* {
+    return reinterpret_cast<double*>(base) + (epoch & 1ull) * n_all;
   };
   for (int64_t i = threadIdx.x; i < p.B_local * S; i += kThreads) {
     const long long v = (long long)__ldcg(p.acc + i);
@@ -528,13 +590,13 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   if ((int)threadIdx.x < p.world) {
     const int q = threadIdx.x;
     unsigned long long* theirs = flags_of(__ldg(p.peer_bases + q)) + p.rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(p.epoch) : "memory");
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
     const unsigned long long* mine = flags_of(__ldg(p.peer_bases + p.rank)) + q;
     unsigned long long seen = 0ull, t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (true) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-      if (seen >= p.epoch) break;
+      if (seen >= epoch) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived -- give up instead of hanging the GPU
         s_timeout = 1;
@@ -545,6 +607,7 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   }
   __syncthreads();
   __threadfence();
+  if (threadIdx.x == 0) __stcg(my_step, epoch);  // all threads have read it (barrier above)
   LossParams full = p;
   full.inst_stats = slot_of(__ldg(p.peer_bases + p.rank));
   if (p.inst_stats)
@@ -621,18 +684,29 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     }
   }
 #endif
-  if (STATS && p.finalize && epi_two_phase(p)) epi_fill(p, s_epi);
   const double g = (GRAD && p.grad_scale) ? (double)__ldg(p.grad_scale) : 1.0;
+  const float gV = (float)g / (float)V;
+  const bool fill = STATS && p.finalize && epi_two_phase(p);  // inputs of the finishing CTA's epilogue
+  const bool uniform_inst = p.groups == p.B_local && V < 0x70000000LL;
 
   // gradient coefficients that do not depend on the instance
   float coef[CC];
 #pragma unroll
   for (int c = 0; c < CC; ++c) coef[c] = 0.f;
   float mean_s = 1.f;
+  DpPrologue home{1.f, 0.f, false};
+  if (p.mode == kModeDP && p.dp_outputs) {
+    if (GRAD || fill) {
+      home = dp_prologue(p, s_epi, GRAD, fill, uniform_inst ? (int)blockIdx.x / ((int)gridDim.x / p.groups) : -1, gV,
+                         s_scratch);
+      mean_s = home.mean_s;
+    }
+  } else if (fill) {
+    epi_fill(p, s_epi);
+  }
+  DS_STAMP(9);
   if (GRAD) {
-    if (p.mode == kModeDP) {
-      mean_s = batch_mean_sigmoid(p, s_scratch);
-    } else if (p.mode == kModeCE) {
+    if (p.mode == kModeCE) {
       double den = 0.0;
       for (int c = 0; c < nc; ++c) den += (double)__ldg(p.class_w + c) * __ldg(p.class_counts + c);
 #pragma unroll
@@ -641,7 +715,6 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     }
   }
   // coefficient g * w_b / V of instance b (kModeDP / kModeBwd), recomputed when a warp changes instance
-  const float gV = (float)g / (float)V;
   auto instance_coef = [&](int b) -> float {
     if (!GRAD || p.mode == kModeCE) return 0.f;
     if (p.mode == kModeBwd) return gV * __ldg(p.bare_weight + b * p.weight_stride);
@@ -752,7 +825,7 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
 
   // ---- step schedule: group range, interleaved among the group's warps ---------------------------
   int cur_b = -1;
-  if (p.groups == p.B_local && V < 0x70000000LL) {
+  if (uniform_inst) {
     // one group per instance (the normal case): the instance is a CTA-uniform value, the base pointers
     // live in uniform registers and a 32-bit voxel offset is all a lane carries from step to step
     const int per_group = (int)gridDim.x / p.groups;
@@ -768,7 +841,7 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     unsigned off = (wg * 32u + lane) * VEC;
     if (wg < n_steps) {
       cur_b = b;
-      coef0 = instance_coef(b);
+      coef0 = home.have_home ? home.coef_home : instance_coef(b);
     }
     DS_STAMP(1);
     // static part: warp w takes steps w, w + W, ... -- all of them, or (dynamic tail) the first dyn_static
@@ -792,7 +865,7 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     // next step is in flight while the current one is processed.
     if (p.claims) {
       cur_b = b;
-      if (wg >= n_steps) coef0 = instance_coef(b);
+      if (wg >= n_steps) coef0 = home.have_home ? home.coef_home : instance_coef(b);
       const unsigned sub = threadIdx.x >> 5;
       unsigned int* ctr = p.claims + ((size_t)b * kWarps + sub) * kTicketStride;
       unsigned pending = 0u;

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   constexpr int kStageBytes = C * kPlaneBytes + kLabelBytes;
   extern __shared__ __align__(128) unsigned char s_ring[];  // kTmaStages x kStageBytes
   __shared__ __align__(8) uint64_t s_full[kTmaStages], s_empty[kTmaStages];
+  __shared__ int s_tile[kTmaStages];
   __shared__ double s_scratch[kWarps + 1];
 
   __shared__ EpiShared s_epi;
@@ -111,17 +112,41 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   const int b = (int)blockIdx.x / per_group;
   const int j0 = (int)blockIdx.x - b * per_group;
   const int64_t n_tiles = (V + kTileV - 1) / kTileV;
-  const int64_t my_tiles = j0 < n_tiles ? (n_tiles - j0 + per_group - 1) / per_group : 0;
   const LT* __restrict__ zb = reinterpret_cast<const LT*>(p.logits) + (int64_t)b * nc * V;
   LT* __restrict__ gb = reinterpret_cast<LT*>(p.dlogits) + (int64_t)b * nc * V;
   const TT* __restrict__ tb = reinterpret_cast<const TT*>(p.target) + (int64_t)b * V;
+
+  // Tile order of this CTA.  Static: j0, j0 + G, j0 + 2G, ...  Dynamic tail (p.claims): the first
+  // p.dyn_static rounds (~80 % of the instance) are static, every later tile is the next unclaimed one of
+  // the instance, taken from the instance's counter by the producer thread one tile ahead of its use
+  // (claiming every tile was slower: 56 vs 52 us on cfg2 fp16 -- the claim sits on the producer's path).  Equal static shares do not finish together under a
+  // saturated memory system (CTAs drift several us apart, the kernel ends with the slowest); claiming in
+  // address order keeps the front narrow.  s_tile[stage] carries the tile index to the consumers; -1 ends.
+  const bool dynamic = p.claims != nullptr;
+  unsigned int* ctr = dynamic ? p.claims + (size_t)b * kWarps * kTicketStride : nullptr;
+  const int64_t k_static = dynamic ? (int64_t)p.dyn_static : 0;  // static rounds (>= kTmaStages - 1, host)
+  const int64_t dyn_base = k_static * per_group;
+  unsigned pending = 0u;      // producer thread: ticket claimed for the next dynamic tile
+  bool prod_done = false;     // producer thread: the instance has no tiles left
 
   // producer side (thread 0): fill stage (k % kTmaStages) with this CTA's k-th tile
   auto produce = [&](int64_t k) {
     const int s = (int)(k % kTmaStages);
     const unsigned round = (unsigned)(k / kTmaStages);
+    int64_t ti = (int64_t)j0 + k * per_group;
+    if (dynamic && k >= k_static) {
+      ti = dyn_base + (int64_t)pending;
+      pending = atomicAdd(ctr, 1u);  // in flight until the next call
+    }
     if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1u);  // all warps hold the previous occupant in registers
-    const int64_t v0 = ((int64_t)j0 + k * per_group) * kTileV;
+    if (ti >= n_tiles) {
+      s_tile[s] = -1;
+      prod_done = true;
+      mbar_arrive(&s_full[s]);
+      return;
+    }
+    s_tile[s] = (int)ti;
+    const int64_t v0 = ti * kTileV;
     const int64_t nv = (V - v0) < kTileV ? (V - v0) : kTileV;
     unsigned char* st = s_ring + (size_t)s * kStageBytes;
     mbar_expect_tx(&s_full[s], (unsigned)(nv * (C * (int64_t)sizeof(LT) + (int64_t)sizeof(TT))));
@@ -138,39 +163,38 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
     for (int s = 0; s < kTmaStages; ++s) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], kWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const int64_t pre = my_tiles < kTmaStages - 1 ? my_tiles : kTmaStages - 1;
-    for (int64_t k = 0; k < pre; ++k) produce(k);
+    if (dynamic) pending = atomicAdd(ctr, 1u);
+    for (int64_t k = 0; k < kTmaStages - 1 && !prod_done; ++k) produce(k);
   }
-  if (p.finalize && epi_two_phase(p)) epi_fill(p, s_epi);
-
   const double g = (GRAD && p.grad_scale) ? (double)__ldg(p.grad_scale) : 1.0;
+  const float gV = (float)g / (float)V;
+  const bool fill = p.finalize && epi_two_phase(p);  // inputs of the finishing CTA's epilogue
   float coef[CC];
-  float mean_s = 1.f;
+  float coef0 = 0.f;
 #pragma unroll
   for (int c = 0; c < CC; ++c) coef[c] = 0.f;
-  if (GRAD) {
-    if (p.mode == kModeDP) {
-      mean_s = batch_mean_sigmoid(p, s_scratch);
-    } else if (p.mode == kModeCE) {
+  if (p.mode == kModeDP && p.dp_outputs) {
+    if (GRAD || fill) {
+      const DpPrologue home = dp_prologue(p, s_epi, GRAD, fill, b, gV, s_scratch);
+      coef0 = home.coef_home;
+      if (GRAD && !home.have_home) {  // batches of more than 64 instances
+        const int64_t bg = p.b_offset + b;
+        const float f = p.fixed_w ? __ldg(p.fixed_w + bg) : 1.0f;
+        coef0 = gV * sigmoid_f(__ldg(p.bare_weight + bg)) / (home.mean_s * f);
+      }
+    }
+  } else {
+    if (fill) epi_fill(p, s_epi);
+    if (GRAD && p.mode == kModeCE) {
       double den = 0.0;
       for (int c = 0; c < nc; ++c) den += (double)__ldg(p.class_w + c) * __ldg(p.class_counts + c);
 #pragma unroll
       for (int c = 0; c < CC; ++c) coef[c] = (float)(g * (double)__ldg(p.class_w + c) / den);
+    } else if (GRAD && p.mode == kModeBwd) {
+      coef0 = gV * __ldg(p.bare_weight + b * p.weight_stride);
     }
   }
   __syncthreads();  // barriers initialised
-
-  float coef0 = 0.f;
-  if (GRAD && p.mode != kModeCE) {
-    const float gV = (float)g / (float)V;
-    if (p.mode == kModeBwd) {
-      coef0 = gV * __ldg(p.bare_weight + b * p.weight_stride);
-    } else {
-      const int64_t bg = p.b_offset + b;
-      const float f = p.fixed_w ? __ldg(p.fixed_w + bg) : 1.0f;
-      coef0 = gV * sigmoid_f(__ldg(p.bare_weight + bg)) / (mean_s * f);
-    }
-  }
 
   constexpr bool PACKED = C == 2;
   constexpr int kHistSteps = 252 / VEC;
@@ -188,11 +212,13 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
     hist = 0u, hist_steps = 0;
   };
 
-  for (int64_t k = 0; k < my_tiles; ++k) {
-    if (threadIdx.x == 0 && k + kTmaStages - 1 < my_tiles) produce(k + kTmaStages - 1);
+  for (int64_t k = 0;; ++k) {
+    if (threadIdx.x == 0 && !prod_done) produce(k + kTmaStages - 1);
     const int s = (int)(k % kTmaStages);
     mbar_wait(&s_full[s], (unsigned)(k / kTmaStages) & 1u);
-    const int64_t v = ((int64_t)j0 + k * per_group) * kTileV + (int64_t)threadIdx.x * VEC;
+    const int ti = s_tile[s];
+    if (ti < 0) break;
+    const int64_t v = (int64_t)ti * kTileV + (int64_t)threadIdx.x * VEC;
     const bool live = v < V;
     const unsigned char* st = s_ring + (size_t)s * kStageBytes;
     Raw<(int)sizeof(LT) * VEC> rz[CC];
@@ -259,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   lab_c[1] += n_t1, lab_c[0] += seen_fast - n_t1;
   tp_c[1] += n_both, tp_c[0] += seen_fast - n_t1 - n_am1 + n_both;
   pred_c[1] += n_am1, pred_c[0] += seen_fast - n_am1;
-  flush_final<CC>(p, my_tiles > 0 ? b : -1, nll_fix, lab_c, pred_c, tp_c);
+  flush_final<CC>(p, b, nll_fix, lab_c, pred_c, tp_c);
   finish_launch(p, s_scratch, &s_epi);
 }
 

@@ -75,8 +75,9 @@ class FusedExchange:
         return cls._cache[key]
 
     def next_epoch(self) -> int:
-        self.epoch += 1
-        return self.epoch
+        """Step counter argument of ``ds_dp_loss_fwd_bwd_exchange``: 0 = the kernel keeps the counter in the
+        exchange buffer itself (no host state, so the step can be captured in a CUDA graph)."""
+        return 0
 
 
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:

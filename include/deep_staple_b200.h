@@ -174,7 +174,8 @@ int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const void* target, 
  * and runs the batch epilogue on the complete [B_total, C, DS_STATS] statistics, so loss_out,
  * d_bare_weight, per_inst_out (and inst_stats, if not NULL) are those of the GLOBAL batch on every
  * rank.  `epoch` is a step counter that is identical on all ranks and starts at 1; all ranks must make
- * the same sequence of calls.  A peer that does not arrive within 10 s yields NaN losses instead of
+ * the same sequence of calls.  epoch == 0 uses (and advances) a counter kept in the exchange buffer
+ * instead, so that the call has no host-side state and can be captured in a CUDA graph.  A peer that does not arrive within 10 s yields NaN losses instead of
  * a hang. */
 size_t ds_dp_loss_exchange_bytes(int64_t B_total, int64_t C, int world);
 

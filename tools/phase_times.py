@@ -46,7 +46,7 @@ def launch(i):
 for i in range(20):
     launch(i)
 torch.cuda.synchronize()
-buf = np.zeros((2048, 10), dtype=np.uint64)
+buf = np.zeros((2048, 16), dtype=np.uint64)
 rows = []
 for rep in range(5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -67,7 +67,7 @@ for rep in range(5):
     line = f"grid {n} event {e0.elapsed_time(e1) * 1000:.1f}us | "
     for k, nm in enumerate(names):
         line += f"{nm} {np.min(rel[:, k]):.1f}/{np.median(rel[:, k]):.1f}/{np.max(rel[:, k]):.1f} "
-    line += f"| last CTA {last}: ticket {rel[last, 6]:.1f} end {rel[last, 7]:.1f}"
+    line += f"| last CTA {last}: ticket {rel[last, 6]:.1f} end {rel[last, 7]:.1f} | fill {np.median(rel[:, 9]):.2f} pro {np.median(rel[:, 1]):.2f} | last: fence {rel[last, 5]:.2f} pre {rel[last, 10]:.2f} ticket {rel[last, 6]:.2f} fence2 {rel[last, 11]:.2f} stats {rel[last, 12]:.2f} end {rel[last, 7]:.2f}"
     print(line)
     if rep == 4 and os.environ.get("DS_DUMP"):
         np.save(os.environ["DS_DUMP"], t)
