@@ -25,11 +25,17 @@ constexpr int kWChunk = 4096;  // candidate weights staged in shared memory per 
 #define DS_VOTE_U8_VPT 16
 #endif
 constexpr int kBatch = DS_VOTE_BATCH;  // candidate planes whose loads are in flight together (divides 16)
+// uint8 planes move 16 bytes per thread and load: Little's law needs twice the loads in flight of the int64
+// path (32 bytes per thread and load) to cover the same HBM latency x bandwidth product
+#ifndef DS_VOTE_U8_BATCH
+#define DS_VOTE_U8_BATCH 16
+#endif
 
 template <typename LT, bool VECP>
 struct VoteIn;
 template <>
 struct VoteIn<int64_t, true> {
+  static constexpr int kBatchN = kBatch;
   static constexpr bool kBinaryPath = true;  // also makes the label test wait for ALL loads of the batch
   static constexpr int VPT = 4;  // 2 x 16 B
   struct Raw {
@@ -54,6 +60,7 @@ struct VoteIn<int64_t, true> {
 };
 template <>
 struct VoteIn<int64_t, false> {
+  static constexpr int kBatchN = kBatch;
   static constexpr bool kBinaryPath = false;
   static constexpr int VPT = 1;
   struct Raw {
@@ -68,6 +75,7 @@ struct VoteIn<int64_t, false> {
 };
 template <>
 struct VoteIn<uint8_t, true> {
+  static constexpr int kBatchN = DS_VOTE_U8_BATCH;
   static constexpr bool kBinaryPath = true;  // 1 B per voxel-candidate: instruction issue is the limit
   static constexpr int VPT = DS_VOTE_U8_VPT;  // one 16 B (or 8 B) load
   static constexpr int W = VPT / 4;
@@ -109,6 +117,7 @@ struct VoteIn<uint8_t, true> {
 };
 template <>
 struct VoteIn<uint8_t, false> {
+  static constexpr int kBatchN = kBatch;
   static constexpr bool kBinaryPath = false;
   static constexpr int VPT = 1;
   struct Raw {
@@ -296,12 +305,13 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
             }
           }
         };
+        constexpr int kB = In::kBatchN;
         int nb = 0;
-        for (; nb + kBatch <= nn; nb += kBatch) {
-          batch(std::integral_constant<int, kBatch>{}, nb);
+        for (; nb + kB <= nn; nb += kB) {
+          batch(std::integral_constant<int, kB>{}, nb);
           // ATen cascade: after every full block of 16 rows fold level 0 into level 1, after
           // every 256 rows level 1 into level 2, after every 4096 rows level 2 into level 3
-          const int64_t done = n0 + nb + kBatch;
+          const int64_t done = n0 + nb + kB;
           if constexpr (LEVELS > 1) {
             if ((done & 15) == 0) {
 #pragma unroll
@@ -320,10 +330,13 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
           }
         }
         // tail of N (never completes a block of 16: kBatch divides 16)
-        if constexpr (kBatch > 4) {
+        if constexpr (kB > 8) {
+          if (nn - nb >= 8) batch(std::integral_constant<int, 8>{}, nb), nb += 8;
+        }
+        if constexpr (kB > 4) {
           if (nn - nb >= 4) batch(std::integral_constant<int, 4>{}, nb), nb += 4;
         }
-        if constexpr (kBatch > 2) {
+        if constexpr (kB > 2) {
           if (nn - nb >= 2) batch(std::integral_constant<int, 2>{}, nb), nb += 2;
         }
         if (nn - nb >= 1) batch(std::integral_constant<int, 1>{}, nb), nb += 1;
