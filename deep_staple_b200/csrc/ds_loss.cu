@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(kThreads) label_stats_kernel(const LossParams 
       }
     }
   }
-  flush_final<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c);
-  finish_launch(p, s_scratch);
+  const bool by_warp0 = flush_final<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c);
+  finish_launch(p, s_scratch, nullptr, by_warp0);
 }
 
 }  // namespace

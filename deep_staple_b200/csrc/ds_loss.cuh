@@ -448,20 +448,25 @@ __device__ __forceinline__ void flush_instance(const LossParams& p, int b, long 
 // End-of-kernel flush: normally all warps of a CTA end in the same instance -> reduce the CTA in
 // shared memory first and issue ONE atomic per statistic per CTA (same-address atomics serialise at
 // the L2, ~27 cycles each).  Warps in different instances fall back to per-warp flushes.
+// Returns true when every global atomic of this CTA was issued by warp 0 (the fence before the arrival
+// ticket is then warp 0's alone).  `uniform`: the caller knows that all warps hold instance cur_b (CTA-uniform).
 template <int CC>
-__device__ __forceinline__ void flush_final(const LossParams& p, int cur_b, long long (&nll_fix)[CC], int (&lab_c)[CC],
-                                            int (&pred_c)[CC], int (&tp_c)[CC]) {
+__device__ __forceinline__ bool flush_final(const LossParams& p, int cur_b, long long (&nll_fix)[CC], int (&lab_c)[CC],
+                                            int (&pred_c)[CC], int (&tp_c)[CC], bool uniform = false) {
   __shared__ long long s_acc[kWarps][32];
   __shared__ int s_b;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_b = cur_b;
-  __syncthreads();
-  const int b0 = s_b;
-  if (!__syncthreads_and(cur_b == b0)) {
-    if (cur_b >= 0) flush_instance<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c);
-    return;
+  int b0 = cur_b;
+  if (!uniform) {
+    if (threadIdx.x == 0) s_b = cur_b;
+    __syncthreads();
+    b0 = s_b;
+    if (!__syncthreads_and(cur_b == b0)) {
+      if (cur_b >= 0) flush_instance<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c);
+      return false;
+    }
   }
-  if (b0 < 0) return;
+  if (b0 < 0) return true;
 #pragma unroll
   for (int c = 0; c < CC; ++c) {
     if (c < p.C) {
@@ -482,23 +487,39 @@ __device__ __forceinline__ void flush_final(const LossParams& p, int cur_b, long
     for (int w = 0; w < kWarps; ++w) t += s_acc[w][threadIdx.x];
     if (t) atomicAdd(p.acc + (int64_t)b0 * p.C * kStatsPerClass + threadIdx.x, (unsigned long long)t);
   }
+  return true;
 }
 
 // Kernel tail: the last CTA to finish turns the integer statistics into the [B, C, 4] doubles of
 // the ABI, zeroes the workspace for the next launch and (single-GPU) runs the batch epilogue.
-__device__ __forceinline__ void finish_launch(const LossParams& p, double* scratch, EpiShared* epi = nullptr) {
+// arrival ticket with acquire-release semantics at gpu scope: the statistics this CTA added are visible to
+// whoever observes the ticket, and the finishing CTA sees everybody's without a second fence
+__device__ __forceinline__ unsigned ticket_acq_rel(unsigned int* counter) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+  return old;
+}
+__device__ __forceinline__ void finish_launch(const LossParams& p, double* scratch, EpiShared* epi = nullptr,
+                                              bool warp0_only = false) {
   __shared__ int s_last;
   // `epi` was filled in the kernel prologue (epi_fill) iff the launch finalizes a batch of <= kThreads
   const bool two_phase = epi && p.finalize && epi_two_phase(p);
   EpiPre pre{};
-  __threadfence();
-  __syncthreads();
+  if (warp0_only) {
+    // all of this CTA's statistics atomics came from warp 0 (flush_final): only that warp has anything to
+    // publish, the gradient stores of the others need not have landed before the ticket
+    if (threadIdx.x < 32) __threadfence();
+    __syncwarp();
+  } else {
+    __threadfence();
+    __syncthreads();
+  }
   DS_STAMP(5);
   const bool single = gridDim.x <= (unsigned)kSingleTicketGrid;
   unsigned ticket = 0u;
   // one persistent wave: arrivals are spread over the CTAs' finish times, one counter is enough and
   // saves the last CTA a fence + a second atomic round trip (~1.4 us of pure tail)
-  if (single && threadIdx.x == 0) ticket = atomicAdd(p.counters, 1u);
+  if (single && threadIdx.x == 0) ticket = ticket_acq_rel(p.counters);
   // the statistics-independent half of the epilogue (all its divisions) runs while the ticket is in flight
   if (two_phase) pre = epi_pre(p, *epi);
   DS_STAMP(10);
@@ -528,7 +549,7 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   __syncthreads();
   DS_STAMP(6);
   if (!s_last) return;
-  __threadfence();
+  if (!single) __threadfence();  // the single ticket was an acquire (thread 0) + the barrier above
   DS_STAMP(11);
   if (p.claims)  // every CTA has stopped claiming: leave the counters clean for the next launch
     for (int i = threadIdx.x; i < (int)p.B_local * kWarps; i += kThreads) p.claims[(size_t)i * kTicketStride] = 0u;
@@ -905,9 +926,9 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
   if (STATS) {
     if constexpr (PACKED) empty_hist();
     merge_fast();
-    flush_final<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c);
+    const bool by_warp0 = flush_final<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c, uniform_inst && p.claims != nullptr);
     DS_STAMP(4);
-    finish_launch(p, s_scratch, &s_epi);
+    finish_launch(p, s_scratch, &s_epi, by_warp0);
   }
 }
 

@@ -61,6 +61,50 @@ def main():
             assert g.is_sparse and torch.equal(g.indices(), g1.indices())  # ALL global rows on every rank
             close(g.values(), g1.values(), 1e-6, what + " sparse data-parameter gradient")
             close(z.grad, z1.grad[sl], 1e-6, what + " local logits gradient")
+    # ---- the fused-exchange step has no host-side state (epoch 0 = counter in the exchange buffer): it can be
+    # captured in a CUDA graph and replayed; every replayed step must reproduce the single-GPU loss
+    from deep_staple_b200 import _binding as b
+
+    lib = b.load()
+    ex = dd.FusedExchange.get(B, C, dev)
+    V = shape[0] * shape[1] * shape[2]
+    z_l, t_l = logits[sl].contiguous(), target[sl].contiguous()
+    bare_g = emb_w.reshape(-1).to(dev)[idx].contiguous()
+    fixed_g = fixed[idx].contiguous()
+    scale = torch.tensor(128.0, device=dev)
+    dz = torch.empty_like(z_l)
+    stats = torch.zeros((B, C, 4), dtype=torch.float64, device=dev)
+    loss_out = torch.zeros(2, device=dev)
+    d_bare = torch.zeros(B, device=dev)
+    per_inst = torch.zeros((B, 4), device=dev)
+    ws = torch.zeros((int(lib.ds_dp_loss_workspace_bytes(B_local, C)) + 7) // 8, dtype=torch.int64, device=dev)
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+
+    def launch(stream):
+        rc = lib.ds_dp_loss_fwd_bwd_exchange(
+            z_l.data_ptr(), b.DS_F32, t_l.data_ptr(), b.DS_I64, None, B_local, C, V, bare_g.data_ptr(),
+            fixed_g.data_ptr(), B, rank * B_local, cw.data_ptr(), 1, scale.data_ptr(), dz.data_ptr(), stats.data_ptr(),
+            loss_out.data_ptr(), d_bare.data_ptr(), per_inst.data_ptr(), ex.peer_bases.data_ptr(), ex.rank, ex.world,
+            0, ws.data_ptr(), ws.numel() * 8, stream)
+        assert rc == 0, lib.ds_last_error_string()
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(3):
+                launch(side.cuda_stream)
+    for rep in range(3):
+        loss_out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        close(loss_out[0], ref.dp_loss, 1e-6, f"graph replay {rep} dp_loss")
+        close(loss_out[1], ref.ce_loss, 1e-6, f"graph replay {rep} ce_loss")
+        assert torch.equal(stats, ref.inst_stats), f"graph replay {rep}: statistics"
+        close(dz, z1.grad[sl], 1e-6, f"graph replay {rep} logits gradient")
+    dist.barrier()
+
     # the global label histogram (normaliser of the class-weighted CE under data parallelism)
     counts = dd.global_class_counts(out.inst_stats[sl, :, 1].sum(0))
     assert torch.equal(counts, torch.bincount(target.reshape(-1), minlength=C).double())

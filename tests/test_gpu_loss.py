@@ -137,6 +137,54 @@ def test_random_vs_oracle(cuda_device, dtype, C, shape):
         assert int(out.inst_stats[:, c, 3].sum()) == int(((pred == c) & (target == c)).sum())
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("B,C,shape", [
+    (33, 2, (32, 64)),        # > 32 instances: block-wide epilogue reduction
+    (64, 2, (256, 256)),      # cfg4 (2D slice mode): dynamic tail with 8 claim counters x 64 instances
+    (70, 2, (16, 64)),        # > 64 instances: data-parameter prologue fallback
+    (300, 2, (8, 16)),        # > 256 instances: generic (loop) epilogue
+    (2, 2, (96, 128, 128)),   # long instances: static rounds + dynamic tail (LDG shell) / TMA shell (fp16)
+    (3, 3, (64, 96, 128)),    # C = 3: TMA shell
+])
+def test_batch_and_schedule_paths_vs_oracle(cuda_device, dtype, B, C, shape):
+    """Every epilogue form (one warp / block / loop), every prologue form (<= 64 instances per warp pass, block
+    sum beyond) and both schedules of the streaming loop (static rounds + per-warp claimed tail, TMA tiles),
+    each against the oracle -- plus bit-identical statistics and outputs on a second run (the claimed tail
+    changes which warp processes which step, never the exact integer sums)."""
+    import deep_staple_b200 as ds
+
+    gen = torch.Generator().manual_seed(77 + B)
+    M = B + 5
+    logits = (2 * torch.randn((B, C, *shape), generator=gen)).to(dtype)
+    target = (torch.rand((B, *shape), generator=gen) * C * 0.6).long().clamp_(0, C - 1)
+    emb_w = torch.randn((M, 1), generator=gen)
+    idx = torch.randperm(M, generator=gen)[:B]
+    fixed = torch.rand(M, generator=gen) * 5 + 1
+    cw = torch.rand(C, generator=gen) + 0.5
+    ref = ol.run_loss(logits, target, emb_w, idx, fixed, cw, True, 64.0, True)
+    dev = cuda_device
+    outs = []
+    for _ in range(2):
+        z = logits.to(dev).requires_grad_(True)
+        bare = emb_w.reshape(-1)[idx].to(dev).requires_grad_(True)
+        out = ds.dp_weighted_loss(z, target.to(dev), bare, fixed[idx].to(dev), True, grad_scaler=64.0,
+                                  class_weights=cw.to(dev), return_all=True)
+        (out.dp_loss * 64.0).backward()
+        outs.append((out, z.grad.clone(), bare.grad.clone()))
+    out, dz, dbare = outs[0]
+    _close(out.dp_loss, ref.dp_loss, LOSS_RTOL, "dp_loss")
+    _close(out.ce_loss, ref.ce_loss, LOSS_RTOL, "ce_loss")
+    _close(out.per_instance_ce, ref.per_inst_ce, LOSS_RTOL, "per_instance_ce")
+    assert torch.equal(out.fg_pred.cpu().long(), ref.fg_pred)
+    _close(dbare, ref.d_bare_weight, GRAD_RTOL, "d_bare_weight")
+    # fp16 gradients below 6.1e-5 are subnormal (absolute step 5.96e-8): the long instances land there at scale 64
+    _close(dz.float(), ref.d_logits.float(), 2e-3 if dtype == torch.float16 else GRAD_RTOL, "d_logits",
+           atol=6e-8 if dtype == torch.float16 else 0.0)
+    out2, dz2, dbare2 = outs[1]
+    assert torch.equal(out.inst_stats, out2.inst_stats) and torch.equal(out.dp_loss, out2.dp_loss)
+    assert torch.equal(dz, dz2) and torch.equal(dbare, dbare2)
+
+
 def test_cfg2_full_size_vs_oracle(cuda_device):
     """BASELINE.json configs[1]: batch 8 x 2 classes x 128^3, risk regularisation, fwd+bwd."""
     import deep_staple_b200 as ds
