@@ -265,7 +265,9 @@ extern "C" int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const voi
 
 extern "C" size_t ds_dp_loss_exchange_bytes(int64_t B_total, int64_t C, int world) {
   if (B_total <= 0 || C <= 0 || world <= 0) return 0;
-  return sizeof(double) * 2 * (size_t)B_total * (size_t)C * kStatsPerClass + sizeof(unsigned long long) * ((size_t)world + 1);
+  (void)world;  // the LL layout does not depend on the number of ranks: 2 slots x 16 B + decoded doubles + step counter
+  const size_t n_all = (size_t)B_total * (size_t)C * kStatsPerClass;
+  return 2 * n_all * 16 + n_all * sizeof(double) + sizeof(unsigned long long);
 }
 
 extern "C" int ds_dp_loss_fwd_bwd_exchange(const void* logits, int logit_dtype, const void* target, int target_dtype,

@@ -555,8 +555,8 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
     for (int i = threadIdx.x; i < (int)p.B_local * kWarps; i += kThreads) p.claims[(size_t)i * kTicketStride] = 0u;
   const int S = p.C * kStatsPerClass;
   const double inv_scale = 1.0 / p.nll_scale;
+  __shared__ double s_stats[kSmemStats];  // reduced statistics of the whole batch, when they fit
   if (p.peer_bases == nullptr) {
-    __shared__ double s_stats[kSmemStats];
     const bool staged = p.finalize && p.B_local == p.B_total && p.B_total * S <= kSmemStats;
     for (int64_t i = threadIdx.x; i < p.B_local * S; i += kThreads) {
       const long long v = (long long)__ldcg(p.acc + i);
@@ -580,59 +580,64 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   }
   // ---- fused exchange over NVLink peer memory (data-parallel loss) --------------------------------
   // Every rank owns an exchange buffer mapped into all peers:
-  //   [2][B_total * S] doubles (statistics, double-buffered by step parity) | [world] u64 arrival flags.
-  // This CTA stores the rank's rows straight into EVERY rank's buffer, publishes "rows of step `epoch`
-  // have landed" in each peer's flag word, waits until all peers did the same here, and then runs the
-  // batch epilogue on the complete statistics -- no separate all-gather, no second launch.
-  // A peer can be at most one step ahead (it needs our flag of step k+1 to finish step k+1), so two
-  // statistic slots are enough.
+  //   [2][B_total * S] x 16 B  (statistics, double-buffered by step parity)  |  [B_total * S] doubles  |  u64 step
+  // Each statistic travels as ONE 16-byte store {lo32, tag, hi32, tag} with tag = the step number: every 8-byte
+  // half validates itself (8-byte accesses are atomic), so the receiver simply polls its own slot until both
+  // tags match -- no system-scope fence, no separate flag round trip: the exchange costs one NVLink one-way
+  // latency (the NCCL "LL" idea, here inside the loss kernel's tail).  This CTA stores the rank's rows into EVERY
+  // rank's buffer (its own included), collects all rows from its own buffer and runs the batch epilogue on the
+  // complete statistics -- no all-gather, no second launch.  A peer can be at most one step ahead (it needs our
+  // rows of step k+1 to finish step k+1), so two slots are enough.
   const int64_t n_all = p.B_total * S;
-  auto flags_of = [&](unsigned long long base) -> unsigned long long* {
-    return reinterpret_cast<unsigned long long*>(base) + 2 * n_all;
-  };
-  // step counter: the caller's (epoch > 0) or the one kept behind the flags of this rank's own buffer
-  // (epoch == 0), which makes the launch independent of host state -- CUDA-graph capturable
-  unsigned long long* my_step = flags_of(__ldg(p.peer_bases + p.rank)) + p.world;
+  uint4* const self = reinterpret_cast<uint4*>(__ldg(p.peer_bases + p.rank));
+  double* const decoded = reinterpret_cast<double*>(self + 2 * n_all);
+  // step counter: the caller's (epoch > 0) or the one kept in this rank's own buffer (epoch == 0), which makes
+  // the launch independent of host state -- CUDA-graph capturable
+  unsigned long long* my_step = reinterpret_cast<unsigned long long*>(decoded + n_all);
   const unsigned long long epoch = p.epoch ? p.epoch : __ldcg(my_step) + 1ull;
-  auto slot_of = [&](unsigned long long base) -> double* {
-    return reinterpret_cast<double*>(base) + (epoch & 1ull) * n_all;
-  };
+  const unsigned tag = (unsigned)epoch;
+  const int64_t slot = (int64_t)(epoch & 1ull) * n_all;
   for (int64_t i = threadIdx.x; i < p.B_local * S; i += kThreads) {
     const long long v = (long long)__ldcg(p.acc + i);
     __stcg(p.acc + i, 0ull);
     const double d = ((i % kStatsPerClass) == DS_STAT_NLL) ? (double)v * inv_scale : (double)v;
-    for (int q = 0; q < p.world; ++q) slot_of(__ldg(p.peer_bases + q))[p.b_offset * S + i] = d;
+    const unsigned lo = (unsigned)__double2loint(d), hi = (unsigned)__double2hiint(d);
+    for (int q = 0; q < p.world; ++q) {
+      uint4* dst = reinterpret_cast<uint4*>(__ldg(p.peer_bases + q)) + slot + p.b_offset * S + i;
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(lo), "r"(tag), "r"(hi), "r"(tag)
+                   : "memory");
+    }
   }
-  __threadfence_system();
-  __syncthreads();
   __shared__ int s_timeout;
   if (threadIdx.x == 0) s_timeout = 0;
   __syncthreads();
-  if ((int)threadIdx.x < p.world) {
-    const int q = threadIdx.x;
-    unsigned long long* theirs = flags_of(__ldg(p.peer_bases + q)) + p.rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
-    const unsigned long long* mine = flags_of(__ldg(p.peer_bases + p.rank)) + q;
-    unsigned long long seen = 0ull, t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const bool staged = n_all <= kSmemStats;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int64_t j = threadIdx.x; j < n_all; j += kThreads) {
+    const uint4* src = self + slot + j;
+    uint4 w;
     while (true) {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-      if (seen >= epoch) break;
+      asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(src) : "memory");
+      if (w.y == tag && w.w == tag) break;
+      unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived -- give up instead of hanging the GPU
         s_timeout = 1;
         break;
       }
-      __nanosleep(200);
     }
+    const double d = __hiloint2double((int)w.z, (int)w.x);
+    if (staged) s_stats[j] = d;
+    else decoded[j] = d;
+    if (p.inst_stats) p.inst_stats[j] = d;
   }
+  if (!staged) __threadfence();
   __syncthreads();
-  __threadfence();
   if (threadIdx.x == 0) __stcg(my_step, epoch);  // all threads have read it (barrier above)
   LossParams full = p;
-  full.inst_stats = slot_of(__ldg(p.peer_bases + p.rank));
-  if (p.inst_stats)
-    for (int64_t i = threadIdx.x; i < n_all; i += kThreads) p.inst_stats[i] = __ldcg(full.inst_stats + i);
+  full.inst_stats = decoded;
+  full.stats_smem = staged ? s_stats : nullptr;
   if (two_phase) epi_post(full, *epi, pre);
   else finalize_block(full, scratch);
   if (s_timeout && threadIdx.x == 0 && p.loss_out) p.loss_out[0] = p.loss_out[1] = __int_as_float(0x7fc00000);

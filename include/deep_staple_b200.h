@@ -167,16 +167,17 @@ int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const void* target, 
 
 /* Data-parallel form with the statistics exchange FUSED into the kernel tail (no NCCL call, no
  * second launch): every rank owns an exchange buffer of ds_dp_loss_exchange_bytes(B_total, C, world)
- * bytes (zero-filled once) that is mapped into all peers (NVLink / NVSwitch peer memory, e.g. a
- * torch.distributed._symmetric_memory allocation); `peer_bases` is a DEVICE array [world] with the
+ * bytes (zero-filled once, 16-byte aligned) that is mapped into all peers (NVLink / NVSwitch peer memory,
+ * e.g. a torch.distributed._symmetric_memory allocation); `peer_bases` is a DEVICE array [world] with the
  * address of every rank's buffer as seen from this GPU.  The last CTA stores this rank's rows of the
- * statistics into every rank's buffer, raises its arrival flag there, waits for all peers' flags here
- * and runs the batch epilogue on the complete [B_total, C, DS_STATS] statistics, so loss_out,
- * d_bare_weight, per_inst_out (and inst_stats, if not NULL) are those of the GLOBAL batch on every
- * rank.  `epoch` is a step counter that is identical on all ranks and starts at 1; all ranks must make
- * the same sequence of calls.  epoch == 0 uses (and advances) a counter kept in the exchange buffer
- * instead, so that the call has no host-side state and can be captured in a CUDA graph.  A peer that does not arrive within 10 s yields NaN losses instead of
- * a hang. */
+ * statistics into every rank's buffer -- each value as one 16-byte store {lo32, step, hi32, step}, so every
+ * 8-byte half validates itself and neither a system-scope fence nor a flag round trip is needed -- polls its
+ * own buffer until all rows of this step have arrived and runs the batch epilogue on the complete
+ * [B_total, C, DS_STATS] statistics, so loss_out, d_bare_weight, per_inst_out (and inst_stats, if not NULL)
+ * are those of the GLOBAL batch on every rank.  `epoch` is a step counter that is identical on all ranks and
+ * starts at 1; all ranks must make the same sequence of calls.  epoch == 0 uses (and advances) a counter kept in
+ * the exchange buffer instead, so that the call has no host-side state and can be captured in a CUDA graph.
+ * A peer that does not arrive within 10 s yields NaN losses instead of a hang. */
 size_t ds_dp_loss_exchange_bytes(int64_t B_total, int64_t C, int world);
 
 int ds_dp_loss_fwd_bwd_exchange(const void* logits, int logit_dtype, const void* target, int target_dtype,
