@@ -96,13 +96,17 @@ int setup_geometry(LossParams& p, int logit_dtype, int target_dtype, bool* vec_o
   p.units = vec ? p.V / W : p.V;
   *vec_out = vec;
   // TMA-staged shell (ds_loss_tma.cuh): vector path, statistics on, no separate Dice target, C in {2,3,4},
-  // every bulk copy a multiple of 16 bytes, one group of CTAs per instance.  Measured on B200
-  // (profiles/r01_notes/configs_*.log): it wins wherever a voxel costs many instructions per byte moved --
-  // half-precision logits, uint8 labels, C >= 3 (+12..14 %) -- and loses ~5 % on fp32 / int64 / C = 2, where
-  // the LDG shell's 32 warps per SM matter more than its exposed load latency.  DS_LOSS_TMA=0/1 overrides.
+  // every bulk copy a multiple of 16 bytes, one group of CTAs per instance.  Which shell wins was measured per
+  // variant on B200 after the LDG shell got its dynamic tail (profiles/r01_notes/shell_matrix.log, cfg2 / cfg5
+  // shapes, us TMA vs LDG): fp32 logits with C >= 3 -- 207 vs 229 (C = 3), 164 vs 177 (C = 3, forward only),
+  // 119 vs 135 (C = 4): TMA;  C = 2 half logits + int64 labels with gradients -- 50.2 vs 51.4: TMA;  everything
+  // else LDG: fp32 C = 2 68 vs 74, any forward-only C = 2 launch (fp16 37 vs 43, fp32 45 vs 53, uint8 labels 38
+  // vs 51), uint8 labels with gradients (57.4 vs 57.6, fp16 42 vs 45), half logits with C = 3 (209 vs 255: eight
+  // voxels x three planes per thread cost the TMA shell its registers).  DS_LOSS_TMA=0/1 overrides.
   const bool eligible = vec && stats && !p.dice_target && C >= 2 && C <= 4 && (p.V % 16 == 0) &&
                         p.B_local <= (int64_t)sm_count() * env_int("DS_LOSS_TMA_CTAS_PER_SM", kTmaMinBlocks);
-  const bool heavy = logit_dtype != DS_F32 || target_dtype != DS_I64 || C >= 3;
+  const bool heavy = (C >= 3 && logit_dtype == DS_F32) ||
+                     (C == 2 && logit_dtype != DS_F32 && target_dtype == DS_I64 && p.dlogits != nullptr);
   const int choice = env_int("DS_LOSS_TMA", -1);
   p.use_tma = eligible && (choice < 0 ? heavy : choice != 0);
   const int rc = setup_tiles(p, who, stats);

@@ -130,9 +130,13 @@ if __name__ == "__main__":
     loss_case("cfg2 fp16/uint8 fwd+bwd", 8, 2, S3, torch.float16, torch.uint8)
     loss_case("cfg2 fp32/int64 fwd only (out-of-line)", 8, 2, S3, torch.float32, torch.int64, grad=False)
     loss_case("cfg2 fp16/int64 fwd only (out-of-line)", 8, 2, S3, torch.float16, torch.int64, grad=False)
+    loss_case("cfg2 fp32/uint8 fwd only", 8, 2, S3, torch.float32, torch.uint8, grad=False)
+    loss_case("cfg2 fp16/uint8 fwd only", 8, 2, S3, torch.float16, torch.uint8, grad=False)
     loss_case("cfg4 2D 64x2x256x256 fp32/int64", 64, 2, (256, 256), torch.float32, torch.int64, nsets=8, steps=400)
     loss_case("cfg4 2D 64x2x256x256 fp16/int64", 64, 2, (256, 256), torch.float16, torch.int64, nsets=12, steps=400)
     loss_case("cfg5 8x3x192x160x160 fp32/int64", 8, 3, (192, 160, 160), torch.float32, torch.int64, nsets=2, steps=50)
+    loss_case("cfg5 8x3x192x160x160 fp32/int64 fwd only", 8, 3, (192, 160, 160), torch.float32, torch.int64, grad=False, nsets=2, steps=50)
+    loss_case("cfg5 8x3x192x160x160 fp16/int64", 8, 3, (192, 160, 160), torch.float16, torch.int64, nsets=2, steps=50)
     loss_case("cfg5 1x3x192x160x160 fp32/int64 (B=1)", 1, 3, (192, 160, 160), torch.float32, torch.int64, nsets=3)
     loss_case("4-class 8x4x128^3 fp32/int64", 8, 4, S3, torch.float32, torch.int64, nsets=2, steps=100)
     aten_cuda_case("ATen-on-B200 cfg2 fp32/int64 fwd+bwd", 8, 2, S3, torch.float32)
