@@ -221,6 +221,34 @@ def test_cfg2_full_size_vs_oracle(cuda_device):
     assert torch.equal(out2.dp_loss, out.dp_loss) and torch.equal(out2.inst_stats, out.inst_stats)
 
 
+def test_cfg5_instance_size_vs_oracle(cuda_device):
+    """cfg5 (BASELINE.json configs[4]) at its real instance size, 3 classes x 192 x 160 x 160, two instances:
+    the TMA-staged shell over 4800 tiles per instance against the oracle, loss 1e-5 / gradients 1e-4 relative."""
+    import deep_staple_b200 as ds
+
+    gen = torch.Generator().manual_seed(55)
+    B, C, shape, M = 2, 3, (192, 160, 160), 9
+    logits = 2 * torch.randn((B, C, *shape), generator=gen)
+    target = torch.multinomial(torch.tensor([0.94, 0.05, 0.01]), B * math.prod(shape), replacement=True,
+                               generator=gen).reshape(B, *shape)
+    emb_w = torch.randn((M, 1), generator=gen)
+    idx = torch.randperm(M, generator=gen)[:B]
+    fixed = torch.rand(M, generator=gen) * 5 + 1
+    cw = torch.tensor([0.4, 1.3, 2.1])
+    ref = ol.run_loss(logits, target, emb_w, idx, fixed, cw, True, 65536.0, True)
+    dev = cuda_device
+    z = logits.to(dev).requires_grad_(True)
+    bare = emb_w.reshape(-1)[idx].to(dev).requires_grad_(True)
+    out = ds.dp_weighted_loss(z, target.to(dev), bare, fixed[idx].to(dev), True, grad_scaler=65536.0,
+                              class_weights=cw.to(dev), return_all=True)
+    (out.dp_loss * 65536.0).backward()
+    _close(out.dp_loss, ref.dp_loss, LOSS_RTOL, "dp_loss")
+    _close(out.ce_loss, ref.ce_loss, LOSS_RTOL, "ce_loss")
+    assert torch.equal(out.fg_pred.cpu().long(), ref.fg_pred)
+    _close(bare.grad, ref.d_bare_weight, GRAD_RTOL, "d_bare_weight")
+    _close(z.grad, ref.d_logits, GRAD_RTOL, "d_logits")
+
+
 def test_two_pass_backward_matches_fused(cuda_device):
     import deep_staple_b200 as ds
 
