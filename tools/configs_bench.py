@@ -55,6 +55,57 @@ def loss_case(name, B, C, S, ldt, tdt, grad=True, nsets=3, steps=200):
           f"({B * V / sec / 1e9:7.1f} Gvox/s, rotating {ws_mb:.0f} MB)", flush=True)
 
 
+def ce_case(name, B, C, S, ldt, counts_known, nsets=3, steps=100):
+    """Row a1 (main_deep_staple.py:716-719): class-weighted CE value + dlogits through the public API
+    (ds.weighted_ce + backward).  Without `class_counts` the op first histograms the labels (one extra read of
+    the labels: 8 B per voxel on top of the 24), with them (e.g. from the data loader) it is one launch."""
+    V = math.prod(S)
+    sets = []
+    for i in range(nsets):
+        g = torch.Generator(device=dev).manual_seed(i)
+        z = (2 * torch.randn((B, C, *S), generator=g, device=dev)).to(ldt).requires_grad_(True)
+        t = (torch.rand((B, *S), generator=g, device=dev) < 0.05).long()
+        sets.append((z, t, torch.bincount(t.reshape(-1), minlength=C).double()))
+    cw = torch.tensor([0.6, 1.4] + [1.0] * (C - 2), device=dev)[:C]
+    state = {"i": 0}
+
+    def fn():
+        z, t, counts = sets[state["i"] % nsets]
+        state["i"] += 1
+        loss = ds.weighted_ce(z, t, cw, grad_scaler=1024.0, class_counts=counts if counts_known else None)
+        (loss * 1024.0).backward()
+        z.grad = None
+
+    sec = bench.timed(fn, steps, 5) / steps
+    alg = B * V * (2 * C * sets[0][0].element_size() + 8 + (0 if counts_known else 8))
+    # the kernel(s) alone through the C ABI (what the GPU does; the Python layer above is host-bound at this size)
+    cwf = cw.float().contiguous()
+    stats = torch.zeros((B, C, 4), dtype=torch.float64, device=dev)
+    loss_out = torch.zeros(2, device=dev)
+    scale = torch.tensor(1024.0, device=dev)
+    ws = torch.zeros((int(lib.ds_dp_loss_workspace_bytes(B, C)) + 7) // 8, dtype=torch.int64, device=dev)
+    grads = [torch.empty_like(z.detach()) for z, _, _ in sets]
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    lstats = torch.zeros((B, C, 4), dtype=torch.float64, device=dev)
+
+    def raw():
+        k = state["i"] % nsets
+        z, t, counts = sets[k]
+        state["i"] += 1
+        if not counts_known:
+            rc = lib.ds_label_stats(t.data_ptr(), b.DS_I64, None, b.DS_I64, B, C, V, lstats.data_ptr(), ws.data_ptr(),
+                                    ws.numel() * 8, stream)
+            assert rc == 0, lib.ds_last_error_string()
+        rc = lib.ds_weighted_ce_fwd_bwd(z.data_ptr(), DT[ldt], t.data_ptr(), b.DS_I64, B, C, V, cwf.data_ptr(),
+                                        counts.data_ptr(), scale.data_ptr(), grads[k].data_ptr(), stats.data_ptr(),
+                                        loss_out.data_ptr(), ws.data_ptr(), ws.numel() * 8, stream)
+        assert rc == 0, lib.ds_last_error_string()
+
+    ksec = bench.timed(raw, steps, 5) / steps
+    print(f"{name:44s} {ksec * 1e6:9.1f} us  {alg / ksec / 1e9:8.1f} GB/s  frac {alg / ksec / 1e9 / peak:5.3f}  "
+          f"({B * V / ksec / 1e9:7.1f} Gvox/s)  [C ABI; public API incl. autograd, host-bound: {sec * 1e6:.0f} us]", flush=True)
+
+
 def vote_case(name, T, N, S, dt, steps=20, nsets=1):
     V = math.prod(S)
     g = torch.Generator(device=dev).manual_seed(1)
@@ -121,7 +172,7 @@ def _wrap(fn):
 
 if __name__ == "__main__":
     # DS_CASES=substr[,substr...] runs only the matching cases
-    loss_case, vote_case, aten_cuda_case = _wrap(loss_case), _wrap(vote_case), _wrap(aten_cuda_case)
+    loss_case, vote_case, aten_cuda_case, ce_case = _wrap(loss_case), _wrap(vote_case), _wrap(aten_cuda_case), _wrap(ce_case)
     S3 = (128, 128, 128)
     loss_case("cfg2 fp32/int64 fwd+bwd", 8, 2, S3, torch.float32, torch.int64)
     loss_case("cfg2 fp16/int64 fwd+bwd (AMP)", 8, 2, S3, torch.float16, torch.int64)
@@ -139,6 +190,9 @@ if __name__ == "__main__":
     loss_case("cfg5 8x3x192x160x160 fp16/int64", 8, 3, (192, 160, 160), torch.float16, torch.int64, nsets=2, steps=50)
     loss_case("cfg5 1x3x192x160x160 fp32/int64 (B=1)", 1, 3, (192, 160, 160), torch.float32, torch.int64, nsets=3)
     loss_case("4-class 8x4x128^3 fp32/int64", 8, 4, S3, torch.float32, torch.int64, nsets=2, steps=100)
+    ce_case("a1 weighted CE cfg2 fp32, counts given", 8, 2, S3, torch.float32, True)
+    ce_case("a1 weighted CE cfg2 fp32, label pre-pass", 8, 2, S3, torch.float32, False)
+    ce_case("a1 weighted CE cfg2 fp16, counts given", 8, 2, S3, torch.float16, True)
     aten_cuda_case("ATen-on-B200 cfg2 fp32/int64 fwd+bwd", 8, 2, S3, torch.float32)
     aten_cuda_case("ATen-on-B200 cfg2 fp16/int64 fwd+bwd", 8, 2, S3, torch.float16)
     vote_case("cfg1 vote 1x10x128^3 int64", 1, 10, S3, torch.int64, steps=200, nsets=4)
