@@ -127,3 +127,16 @@ def test_snapshot_format_round_trip(tmp_path):
     assert torch.equal(back["modified_labels"][0].to_dense(), mod[1])
     groups = ds.group_snapshot(back)
     assert list(groups.keys()) == ["126l", "127r"] and set(groups["126l"].keys()) == {"expert_label", "prediction", "103r", "102l"}
+
+
+def test_bench_graph_chunking_times_exactly_k_steps():
+    """bench.py replays its K timed steps from a CUDA graph of `chunk` steps: chunk must divide K exactly
+    (the contract is EXACTLY K steps between the events), small K is captured whole, and awkward K (no
+    useful divisor) falls back to one launch per step."""
+    import bench
+
+    for k in (1, 2, 7, 50, 250, 256, 2000, 3000, 1024):
+        c = bench.graph_chunk(k)
+        assert c >= 1 and k % c == 0 and c <= max(k, 256) and (c == k or c <= 256), (k, c)
+    assert bench.graph_chunk(2000) == 250
+    assert bench.graph_chunk(257) == 0 and bench.graph_chunk(2 * 257) == 0  # primes beyond the cap: stream launches
