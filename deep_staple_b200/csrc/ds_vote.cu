@@ -376,6 +376,19 @@ int launch_vote(const VoteParams& p0, cudaStream_t stream) {
   // 16 waves measured 6.8 TB/s vs 6.5 TB/s for 4), but every CTA pays the softmax prologue, so a CTA should
   // own at least ~256 / (N * VPT) steps (a step costs N * VPT voxel-candidates per thread) -- unless that
   // would leave SMs without a CTA (few targets): then one wave.
+  const size_t smem = (size_t)(p.N < kWChunk ? p.N : kWChunk) * sizeof(float);
+  const bool ties = p.near_ties != nullptr;
+  const int levels = p.N < 32 ? (p.N < 16 ? 1 : 2) : (p.N < 256 ? 2 : 4);
+  void (*kern)(const VoteParams) = nullptr;
+#define DS_VOTE_PICK(L, TI) kern = vote_kernel<LT, OT, L, TI, VECP>
+  if (levels == 1) {
+    if (ties) DS_VOTE_PICK(1, true); else DS_VOTE_PICK(1, false);
+  } else if (levels == 2) {
+    if (ties) DS_VOTE_PICK(2, true); else DS_VOTE_PICK(2, false);
+  } else {
+    if (ties) DS_VOTE_PICK(4, true); else DS_VOTE_PICK(4, false);
+  }
+#undef DS_VOTE_PICK
   const int sms = sm_count();
   const int per_sm = env_int("DS_VOTE_CTAS_PER_SM", 4), waves = env_int("DS_VOTE_WAVES", 16);
   const int64_t max_chunks = (p.units + kThreads - 1) / kThreads;
@@ -387,24 +400,45 @@ int launch_vote(const VoteParams& p0, cudaStream_t stream) {
     const int64_t one_wave = ((int64_t)sms * per_sm + p.T - 1) / p.T;
     if (by_iters < one_wave) by_iters = one_wave;
     if (want > by_iters) want = by_iters;
+    // Few targets (the notebook's one-target call, cfg1): the grid is only a handful of waves of the CTAs that
+    // are really resident (2 per SM at 108-128 registers), and both the last wave and the last 256-unit
+    // iteration of a CTA can be mostly empty -- 1 target x 30 candidates ran 960 CTAs = 3.2 waves of 3
+    // iterations at 0.79 of HBM.  Model the launch as ceil(waves) x ceil(iterations per CTA) and take the
+    // cheapest whole number of resident waves (cfg1: one wave of 296 CTAs x 6.9 iterations).
+    static thread_local void (*occ_kern)(const VoteParams) = nullptr;  // one query per kernel variant, not per launch
+    static thread_local size_t occ_smem = 0;
+    static thread_local int occ_cached = 0;
+    if (occ_kern != kern || occ_smem != smem) {
+      int o = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem) != cudaSuccess || o < 1) o = 2;
+      occ_kern = kern, occ_smem = smem, occ_cached = o;
+    }
+    const int occ = occ_cached;
+    const int64_t slots = (int64_t)sms * occ;
+    if (p.T * want < 8 * slots && env_int("DS_VOTE_FIT_WAVES", 1)) {
+      auto cost = [&](int64_t w) {
+        const int64_t ctas = p.T * w, per_cta = (p.units + w - 1) / w;
+        return (double)((ctas + slots - 1) / slots) * (double)((per_cta + kThreads - 1) / kThreads);
+      };
+      int64_t best = want < max_chunks ? want : max_chunks;
+      if (best < 1) best = 1;
+      double best_cost = cost(best);
+      for (int k = 1; k <= 8; ++k) {
+        int64_t w = k * slots / p.T;
+        if (w < 1) w = 1;
+        if (w > max_chunks) w = max_chunks;
+        const double c = cost(w);
+        if (c < best_cost * 0.999) best = w, best_cost = c;
+      }
+      want = best;
+    }
   }
   if (want > max_chunks) want = max_chunks;
   if (want < 1) want = 1;
   if (p.T * want > 0x7fffffffLL) return fail(DS_ERR_SHAPE, "ds_consensus_vote: T*chunks exceeds the grid limit");
   p.chunks = (int)want;
   const dim3 grid((unsigned)(p.T * want));
-  const size_t smem = (size_t)(p.N < kWChunk ? p.N : kWChunk) * sizeof(float);
-  const bool ties = p.near_ties != nullptr;
-  const int levels = p.N < 32 ? (p.N < 16 ? 1 : 2) : (p.N < 256 ? 2 : 4);
-#define DS_VOTE_LAUNCH(L, TI) vote_kernel<LT, OT, L, TI, VECP><<<grid, kThreads, smem, stream>>>(p)
-  if (levels == 1) {
-    if (ties) DS_VOTE_LAUNCH(1, true); else DS_VOTE_LAUNCH(1, false);
-  } else if (levels == 2) {
-    if (ties) DS_VOTE_LAUNCH(2, true); else DS_VOTE_LAUNCH(2, false);
-  } else {
-    if (ties) DS_VOTE_LAUNCH(4, true); else DS_VOTE_LAUNCH(4, false);
-  }
-#undef DS_VOTE_LAUNCH
+  kern<<<grid, kThreads, smem, stream>>>(p);
   count_launch();
   return check_launch("ds_consensus_vote");
 }
