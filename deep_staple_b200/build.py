@@ -94,6 +94,8 @@ def build_variant(name: str, extra_flags) -> str:
                          capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(res.stderr)
+    for obj in objs:  # variants travel to the GPU box with the snapshot: keep only the library
+        os.remove(obj)
     return lib
 
 

@@ -22,9 +22,11 @@ size_t acc_bytes(int64_t B_local, int64_t C) {
   return (n + 127) / 128 * 128;
 }
 size_t claim_bytes(int64_t B_local) { return sizeof(unsigned int) * kTicketStride * kWarps * (size_t)B_local; }
+// non-finite loss flags, one word per instance and class (ds_loss.cuh: checked_nll)
+size_t flag_bytes(int64_t B_local, int64_t C) { return (sizeof(unsigned int) * (size_t)B_local * (size_t)C + 127) / 128 * 128; }
 
 // Launch geometry of the persistent kernels: warp steps of 32 units; DS_LOSS_CTAS_PER_SM resident CTAs per SM (never more CTAs than there are
-// groups of kWarps tiles); fixed-point scale of the loss sums sized so that V voxels x 2^10 cannot
+// groups of kWarps tiles); fixed-point scale of the loss sums sized so that V voxels x 2^17 cannot
 // overflow 63 bits.
 int setup_tiles(LossParams& p, const char* who, bool stats) {
   (void)who;
@@ -80,7 +82,7 @@ int setup_tiles(LossParams& p, const char* who, bool stats) {
   }
   int bits_v = 0;
   while (((int64_t)1 << bits_v) < p.V) ++bits_v;
-  int e = 62 - bits_v - 10;
+  int e = 62 - bits_v - kNllMeanBits;  // a mean loss of up to 2^17 per voxel fits (fp16 logits cannot exceed it)
   if (e > 40) e = 40;
   if (e < 0) e = 0;
   p.nll_scale = (double)((int64_t)1 << e);
@@ -133,6 +135,8 @@ int carve_workspace(LossParams& p, void* workspace, size_t workspace_bytes, cons
   p.counters = reinterpret_cast<unsigned int*>(workspace);
   p.acc = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + header_bytes());
   p.claims = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + header_bytes() + acc_bytes(p.B_local, p.C));
+  p.flags = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + header_bytes() + acc_bytes(p.B_local, p.C) +
+                                            claim_bytes(p.B_local));
   return 0;
 }
 
@@ -224,7 +228,7 @@ using namespace ds;
 
 extern "C" size_t ds_dp_loss_workspace_bytes(int64_t B_local, int64_t C) {
   if (B_local <= 0 || C <= 0) return 0;
-  return header_bytes() + acc_bytes(B_local, C) + claim_bytes(B_local);
+  return header_bytes() + acc_bytes(B_local, C) + claim_bytes(B_local) + flag_bytes(B_local, C);
 }
 
 namespace {
@@ -253,6 +257,12 @@ int dp_loss_fwd_bwd_impl(const char* who, const void* logits, int logit_dtype, c
   p.B_local = B_local, p.B_total = B_total, p.b_offset = b_offset, p.V = V, p.C = (int)C;
   p.use_risk = use_risk ? 1 : 0, p.mode = kModeDP, p.finalize = (whole || peer_bases) ? 1 : 0, p.dp_outputs = 1;
   p.peer_bases = peer_bases, p.rank = rank, p.world = world, p.epoch = epoch;
+  // how long a rank waits for its peers' statistics before it declares the step lost (sticky, see finish_launch):
+  // generous by default -- ordinary skew (rank 0 validating or checkpointing, a data-loader stall) is minutes
+  {
+    const int timeout_s = env_int("DS_EXCHANGE_TIMEOUT_S", 1800);
+    p.timeout_ns = timeout_s > 0 ? (unsigned long long)timeout_s * 1000000000ull : 0ull;
+  }
   if (int rc = carve_workspace(p, workspace, workspace_bytes, who)) return rc;
   return launch_loss(p, logit_dtype, target_dtype, dlogits != nullptr, true, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -272,9 +282,9 @@ extern "C" int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const voi
 
 extern "C" size_t ds_dp_loss_exchange_bytes(int64_t B_total, int64_t C, int world) {
   if (B_total <= 0 || C <= 0 || world <= 0) return 0;
-  (void)world;  // the LL layout does not depend on the number of ranks: 2 slots x 16 B + decoded doubles + step counter
+  (void)world;  // the LL layout does not depend on the number of ranks: 2 slots x 16 B + decoded doubles + step counter + error word
   const size_t n_all = (size_t)B_total * (size_t)C * kStatsPerClass;
-  return 2 * n_all * 16 + n_all * sizeof(double) + sizeof(unsigned long long);
+  return 2 * n_all * 16 + n_all * sizeof(double) + 2 * sizeof(unsigned long long);  // + step counter + error word
 }
 
 extern "C" int ds_dp_loss_fwd_bwd_exchange(const void* logits, int logit_dtype, const void* target, int target_dtype,

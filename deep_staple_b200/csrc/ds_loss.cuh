@@ -68,6 +68,7 @@ struct LossParams {
   unsigned int* counters;       // workspace header (kWsCounters words, zero between launches)
   unsigned long long* acc;      // workspace: [B_local, C, 4] exact integer statistics (zero between launches)
   unsigned int* claims;         // workspace: [B_local, kWarps] step-claim counters, 128 B apart (zero between launches); null = static
+  unsigned int* flags;          // workspace: [B_local, C] non-finite loss flags, bit 0 = NaN / bit 1 = +inf (zero between launches)
   unsigned dyn_static;          // warp steps of an instance that are scheduled statically (multiple of the group's warp count)
   int64_t B_local, B_total, b_offset, V;
   int64_t units;                // V / VEC
@@ -80,6 +81,7 @@ struct LossParams {
   // fused multi-GPU exchange (ds_dp_loss_fwd_bwd_exchange): peer-mapped exchange buffers, see finish_launch
   const unsigned long long* peer_bases;  // device array [world]: base address of every rank's exchange buffer
   unsigned long long epoch;              // step counter, identical on all ranks, starts at 1
+  unsigned long long timeout_ns;         // how long the finishing CTA waits for a peer's rows (0 = for ever)
   int rank, world;
 };
 
@@ -132,8 +134,9 @@ __device__ __forceinline__ float log1p_pos(float r) {
   const float s = 1.0f + r;
   const int bits = __float_as_int(s);
   const int k = (bits - 0x3f3504f3) >> 23;
-  const float m = __int_as_float(bits - (k << 23));
-  const float f = (k == 0) ? r : (m - 1.0f);
+  // m - 1 with m = s 2^-k (exact): as an fma on s so that a NaN argument stays NaN (same instruction count as
+  // rebuilding m from the bits, which would turn NaN into a finite number)
+  const float f = (k == 0) ? r : fmaf(s, __int_as_float(0x3f800000 - (k << 23)), -1.0f);
   const float z = f * f;
   float y = 7.0376836292e-2f;
   y = fmaf(y, f, -1.1514610310e-1f);
@@ -147,6 +150,143 @@ __device__ __forceinline__ float log1p_pos(float r) {
   y = y * f * z;
   y = fmaf(-0.5f, z, y);
   return fmaf((float)k, 0.69314718056f, f + y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Non-finite logits.  The reference's AMP flow relies on NaN / Inf reaching the loss and the gradients:
+// scaler_dp.step(optimizer_dp) then skips the step and update() backs the scale off
+// (main_deep_staple.py:762-768).  torch's log_softmax (x - max - log sum exp(x - max)) is NaN for ALL classes
+// of a voxel when any of its logits is NaN, when the maximum is +inf (inf - inf) or when all are -inf; a
+// single -inf next to finite logits is well defined (nll = +inf if it is the target's, softmax 0 / 1).
+// The exact fixed-point accumulation cannot hold NaN / inf, and the binary fast math is written for finite
+// differences (exp(-|d|) of a +inf difference is simply 0).  What the streaming loop does about it:
+//   * C > 2 (ds_loss_math.inc): the math is NaN-exact by construction -- the sum of the non-maximal exponentials
+//     starts from (max - max), i.e. NaN exactly when torch's log-softmax is NaN, and log1p_pos keeps NaN -- for
+//     one FADD per voxel; gradients of such a voxel come out NaN for all classes, like torch.
+//   * C == 2: ONE cheap test per lane and step (NaN-propagating max of |z|, half an instruction per logit, folded
+//     into the warp vote that already selects the binary fast path) sends the warp through the general math with
+//     the offending voxels' logits replaced by NaN first (poison_nonfinite).
+//   * a NaN / +inf per-class loss sum of a lane's step (checked after the math: one FMNMX3 per three sums) raises a
+//     flag per (instance, class) in the workspace instead of entering the fixed-point sum; the finishing CTA turns
+//     flagged sums into NaN / +inf doubles, and the batch epilogue propagates them through loss and
+//     data-parameter gradients by plain IEEE arithmetic.  The predicted-class counts of such a step are
+//     corrected to torch.argmax semantics (NaN counts as the maximum, first one wins) in that cold branch.
+// The same checks catch finite logits far beyond fp16's range: the fixed-point format holds a mean loss per
+// voxel of up to 2^17 > 2 * 65504 + ln 8, and a step sum beyond that is reported as +inf.
+// ---------------------------------------------------------------------------------------------
+constexpr float kSuspectLogit = 65530.0f;  // > fp16 max (65504); 2 * 65530 + ln 8 < 2^17
+constexpr int kNllMeanBits = 17;           // fixed point: V voxels x 2^17 fit 62 bits
+// NaN-propagating max(|a|, |b|, |c|): one FMNMX3.NAN with |x| operand modifiers
+__device__ __forceinline__ float amax3_nan(float a, float b, float c) {
+  float d;
+  asm("{.reg .f32 x, y, z;\n abs.f32 x, %1;\n abs.f32 y, %2;\n abs.f32 z, %3;\n max.NaN.f32 %0, x, y, z;}"
+      : "=f"(d)
+      : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+template <int CC, int VEC>
+__device__ __forceinline__ bool lane_suspicious(const float (&z)[CC][VEC], int nc) {
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < CC * VEC; k += 2) {
+    const float v0 = (k / VEC < nc) ? z[k / VEC][k % VEC] : 0.f;
+    const float v1 = (k + 1 < CC * VEC && (k + 1) / VEC < nc) ? z[(k + 1) / VEC % CC][(k + 1) % VEC] : 0.f;
+    acc = amax3_nan(acc, v0, v1);
+  }
+  return !(acc < kSuspectLogit);
+}
+// true when one of this lane's per-class loss sums of the step is NaN, +inf or beyond the fixed-point range
+template <int CC>
+__device__ __forceinline__ bool sums_suspicious(const float (&nll_c)[CC], int nc, float limit) {
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < CC; k += 2)
+    acc = amax3_nan(acc, k < nc ? nll_c[k] : 0.f, (k + 1 < CC && k + 1 < nc) ? nll_c[k + 1] : 0.f);
+  return !(acc < limit);
+}
+// C == 2 careful path, before the per-voxel math: torch semantics for voxels whose log-softmax is NaN (see
+// above).  Counts: the math that follows sees NaN logits and books such a voxel as predicted class 0; the
+// difference to torch.argmax is corrected here.
+template <int CC, int VEC, bool STATS>
+__device__ __forceinline__ void poison_nonfinite(float (&z)[CC][VEC], const int (&td)[VEC], int nc, int (&pred_c)[CC],
+                                                 int (&tp_c)[CC]) {
+  const float inf = __int_as_float(0x7f800000), nan = __int_as_float(0x7fffffff);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    float m = z[0][i];
+    int am = 0;
+#pragma unroll
+    for (int c = 1; c < CC; ++c) {
+      if (c < nc) {
+        const float v = z[c][i];
+        if (m == m && (v != v || v > m)) m = v, am = c;  // torch.argmax: NaN is the maximum, first one wins
+      }
+    }
+    if (!(fabsf(m) < inf)) {  // NaN, max = +inf, or every logit -inf
+#pragma unroll
+      for (int c = 0; c < CC; ++c) z[c][i] = nan;
+      if (STATS) {
+#pragma unroll
+        for (int c = 1; c < CC; ++c) {
+          const int hit = (c < nc && am == c) ? 1 : 0;
+          pred_c[c] += hit, pred_c[0] -= hit;
+          tp_c[c] += (hit && td[i] == c) ? 1 : 0;
+          tp_c[0] -= (hit && td[i] == 0) ? 1 : 0;
+        }
+      }
+    }
+  }
+}
+// A per-class loss sum of a lane's step that the fixed-point accumulator cannot hold raises the
+// (instance, class) flag and contributes nothing.
+__device__ __forceinline__ float checked_nll(float x, unsigned int* flag, float limit) {
+  if (x != x) {
+    atomicOr(flag, 1u);
+    return 0.f;
+  }
+  if (x > limit) {
+    atomicOr(flag, 2u);
+    return 0.f;
+  }
+  return x;
+}
+// C > 2 cold path, after the math flagged a step (sums_suspicious); ONE out-of-line call so that the hot loop
+// only carries the branch around it.  (1) The math's arg-max ignores NaN logits: re-read this lane's voxels from
+// global memory (the registers are long gone) and return, in `delta`, how the predicted-class ([0, CC)) and
+// true-positive ([CC, 2 CC)) counts move for voxels where torch.argmax disagrees.  (2) Flag the loss sums the
+// fixed point cannot take and zero them in `nll`.  Both arrays live in the caller's local memory.
+template <typename LT, typename TT, int CC, int VEC>
+__device__ __noinline__ void flagged_step(const LT* __restrict__ zb, const TT* __restrict__ tdb, int64_t V, int64_t off,
+                                          int nc, unsigned int* flags, float limit, float* __restrict__ nll,
+                                          int* __restrict__ delta) {
+  for (int i = 0; i < VEC; ++i) {
+    float m = Logit<LT>::to_f32(zb[off + i]), mt = m;
+    int am = 0, at = 0;
+    for (int c = 1; c < nc; ++c) {
+      const float v = Logit<LT>::to_f32(zb[(int64_t)c * V + off + i]);
+      if (v > m) m = v, am = c;                            // the streaming math (strict >, NaN never wins)
+      if (mt == mt && (v != v || v > mt)) mt = v, at = c;  // torch.argmax: NaN is the maximum, first one wins
+    }
+    if (am != at) {
+      const int td = (int)tdb[off + i];
+      delta[at] += 1, delta[am] -= 1;
+      if (td == at) delta[CC + at] += 1;
+      if (td == am) delta[CC + am] -= 1;
+    }
+  }
+  for (int c = 0; c < nc; ++c) nll[c] = checked_nll(nll[c], flags + c, limit);
+}
+template <typename LT, typename TT, int CC, int VEC>
+__device__ __forceinline__ void handle_flagged_step(const LT* zb, const TT* tdb, int64_t V, int64_t off, int nc,
+                                                    float (&nll_c)[CC], int (&pred_c)[CC], int (&tp_c)[CC],
+                                                    unsigned int* flags, float limit) {
+  float nll[CC];      // addressable on purpose: local memory, inside this cold branch only
+  int delta[2 * CC];
+#pragma unroll
+  for (int c = 0; c < CC; ++c) nll[c] = nll_c[c], delta[c] = 0, delta[CC + c] = 0;
+  flagged_step<LT, TT, CC, VEC>(zb, tdb, V, off, nc, flags, limit, nll, delta);
+#pragma unroll
+  for (int c = 0; c < CC; ++c) nll_c[c] = nll[c], pred_c[c] += delta[c], tp_c[c] += delta[CC + c];
 }
 
 // The epilogue reads the reduced statistics from shared memory when the finishing CTA staged them there
@@ -193,8 +333,9 @@ __device__ __forceinline__ InstTerms inst_terms(const LossParams& p, int64_t b) 
 __device__ __forceinline__ void write_inst(const LossParams& p, int64_t b, const InstTerms& t, double g, double m,
                                            double L) {
   const double B = (double)p.B_total;
-  // B == 1: weight / weight.mean() == 1 identically, the data parameter gets no gradient
-  const double grad = (p.B_total == 1) ? 0.0 : g * t.s * (1.0 - t.s) * (t.cb - L / B) / m;
+  // B == 1: weight / weight.mean() == 1 identically, the data parameter gets no gradient (0 x c_b: NaN when
+  // the instance's loss is not finite, as in torch)
+  const double grad = (p.B_total == 1) ? 0.0 * t.cb : g * t.s * (1.0 - t.s) * (t.cb - L / B) / m;
   if (p.d_bare_weight) p.d_bare_weight[b] = (float)grad;
   if (p.per_inst_out) {
     float* o = p.per_inst_out + b * DS_INST;
@@ -336,8 +477,9 @@ __device__ __forceinline__ void epi_post(const LossParams& p, EpiShared& e, cons
   }
   const double L = p.dp_outputs ? acc * pre.inv_m : 0.0;  // :757 / :759
   if (on && p.dp_outputs) {
-    // B == 1: weight / weight.mean() == 1 identically, the data parameter gets no gradient
-    const double grad = (B == 1) ? 0.0 : pre.g * pre.s * (1.0 - pre.s) * (cb - L * pre.inv_B) * pre.inv_m;
+    // B == 1: weight / weight.mean() == 1 identically, the data parameter gets no gradient (0 x c_b: NaN when
+    // the instance's loss is not finite, as in torch)
+    const double grad = (B == 1) ? 0.0 * cb : pre.g * pre.s * (1.0 - pre.s) * (cb - L * pre.inv_B) * pre.inv_m;
     if (p.d_bare_weight) p.d_bare_weight[i] = (float)grad;
     if (p.per_inst_out) {
       float* o = p.per_inst_out + (int64_t)i * DS_INST;
@@ -499,6 +641,19 @@ __device__ __forceinline__ unsigned ticket_acq_rel(unsigned int* counter) {
   asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
   return old;
 }
+// Finishing CTA: statistic i of this rank's [B_local, C, 4] block, read from the exact integer accumulators
+// (left zero for the next launch).  A loss sum whose (instance, class) flag was raised by the careful path of
+// the streaming loop comes out as NaN / +inf, like torch's reduction over the same voxels.
+__device__ __forceinline__ double take_stat(const LossParams& p, int64_t i, double inv_scale) {
+  const long long v = (long long)__ldcg(p.acc + i);
+  __stcg(p.acc + i, 0ull);
+  if ((i % kStatsPerClass) != DS_STAT_NLL) return (double)v;
+  unsigned int* flag = p.flags + i / kStatsPerClass;  // one word per (instance, class), read and cleared by this thread
+  const unsigned f = __ldcg(flag);
+  if (f == 0u) return (double)v * inv_scale;
+  __stcg(flag, 0u);
+  return __longlong_as_double((f & 1u) ? 0x7ff8000000000000LL : 0x7ff0000000000000LL);
+}
 __device__ __forceinline__ void finish_launch(const LossParams& p, double* scratch, EpiShared* epi = nullptr,
                                               bool warp0_only = false) {
   __shared__ int s_last;
@@ -559,9 +714,7 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   if (p.peer_bases == nullptr) {
     const bool staged = p.finalize && p.B_local == p.B_total && p.B_total * S <= kSmemStats;
     for (int64_t i = threadIdx.x; i < p.B_local * S; i += kThreads) {
-      const long long v = (long long)__ldcg(p.acc + i);
-      __stcg(p.acc + i, 0ull);
-      const double d = ((i % kStatsPerClass) == DS_STAT_NLL) ? (double)v * inv_scale : (double)v;
+      const double d = take_stat(p, i, inv_scale);
       __stcg(p.inst_stats + p.b_offset * S + i, d);
       if (staged) s_stats[i] = d;
     }
@@ -580,7 +733,7 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   }
   // ---- fused exchange over NVLink peer memory (data-parallel loss) --------------------------------
   // Every rank owns an exchange buffer mapped into all peers:
-  //   [2][B_total * S] x 16 B  (statistics, double-buffered by step parity)  |  [B_total * S] doubles  |  u64 step
+  //   [2][B_total * S] x 16 B  (statistics, double-buffered by step parity)  |  [B_total * S] doubles  |  u64 step  |  u64 error
   // Each statistic travels as ONE 16-byte store {lo32, tag, hi32, tag} with tag = the step number: every 8-byte
   // half validates itself (8-byte accesses are atomic), so the receiver simply polls its own slot until both
   // tags match -- no system-scope fence, no separate flag round trip: the exchange costs one NVLink one-way
@@ -594,13 +747,18 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   // step counter: the caller's (epoch > 0) or the one kept in this rank's own buffer (epoch == 0), which makes
   // the launch independent of host state -- CUDA-graph capturable
   unsigned long long* my_step = reinterpret_cast<unsigned long long*>(decoded + n_all);
+  // Sticky error word: the step at which a peer's rows did not arrive within timeout_ns.  From then on this rank's
+  // replica can no longer be trusted to have made the same updates as its peers, so EVERY output of this and all
+  // later steps is NaN (loss, data-parameter gradients, per-instance outputs, statistics): GradScaler skips the
+  // steps and the host sees it at the latest when it looks at the loss (FusedExchange.check() raises).  The rank
+  // still publishes its own rows, so healthy peers are not held up by it.
+  unsigned long long* my_err = my_step + 1;
+  const bool dead = __ldcg(my_err) != 0ull;
   const unsigned long long epoch = p.epoch ? p.epoch : __ldcg(my_step) + 1ull;
   const unsigned tag = (unsigned)epoch;
   const int64_t slot = (int64_t)(epoch & 1ull) * n_all;
   for (int64_t i = threadIdx.x; i < p.B_local * S; i += kThreads) {
-    const long long v = (long long)__ldcg(p.acc + i);
-    __stcg(p.acc + i, 0ull);
-    const double d = ((i % kStatsPerClass) == DS_STAT_NLL) ? (double)v * inv_scale : (double)v;
+    const double d = take_stat(p, i, inv_scale);
     const unsigned lo = (unsigned)__double2loint(d), hi = (unsigned)__double2hiint(d);
     for (int q = 0; q < p.world; ++q) {
       uint4* dst = reinterpret_cast<uint4*>(__ldg(p.peer_bases + q)) + slot + p.b_offset * S + i;
@@ -617,30 +775,38 @@ __device__ __forceinline__ void finish_launch(const LossParams& p, double* scrat
   for (int64_t j = threadIdx.x; j < n_all; j += kThreads) {
     const uint4* src = self + slot + j;
     uint4 w;
-    while (true) {
+    bool have = false;
+    while (!dead) {
       asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(src) : "memory");
-      if (w.y == tag && w.w == tag) break;
+      if (w.y == tag && w.w == tag) {
+        have = true;
+        break;
+      }
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived -- give up instead of hanging the GPU
+      if (p.timeout_ns && t1 - t0 > p.timeout_ns) {  // a peer never arrived -- give up instead of hanging the GPU
         s_timeout = 1;
         break;
       }
     }
-    const double d = __hiloint2double((int)w.z, (int)w.x);
+    const double d = have ? __hiloint2double((int)w.z, (int)w.x) : __longlong_as_double(0x7ff8000000000000LL);
     if (staged) s_stats[j] = d;
     else decoded[j] = d;
     if (p.inst_stats) p.inst_stats[j] = d;
   }
   if (!staged) __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) __stcg(my_step, epoch);  // all threads have read it (barrier above)
+  if (threadIdx.x == 0) {
+    __stcg(my_step, epoch);  // all threads have read it (barrier above)
+    if (s_timeout) __stcg(my_err, epoch);
+  }
+  // rows that never arrived are NaN: the epilogue below turns that into a NaN loss and NaN gradients for ALL
+  // data parameters (they are coupled through the batch loss), NaN per-instance outputs for the missing rows
   LossParams full = p;
   full.inst_stats = decoded;
   full.stats_smem = staged ? s_stats : nullptr;
   if (two_phase) epi_post(full, *epi, pre);
   else finalize_block(full, scratch);
-  if (s_timeout && threadIdx.x == 0 && p.loss_out) p.loss_out[0] = p.loss_out[1] = __int_as_float(0x7fc00000);
 }
 
 // Static schedule of one warp (see the header comment): steps first, first + stride, ... < hi.
@@ -759,6 +925,7 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
 #pragma unroll
   for (int c = 0; c < CC; ++c) nll_fix[c] = 0, lab_c[c] = 0, pred_c[c] = 0, tp_c[c] = 0;
   const float nll_scale = (float)p.nll_scale;
+  const float nll_limit = (float)(VEC << kNllMeanBits);  // careful path: largest step sum the fixed point takes
   unsigned hist = 0u;
   int hist_steps = 0;
   auto empty_hist = [&]() {  // fields: [t=0,am=0] [t=1,am=0] [t=0,am=1] [t=1,am=1]
@@ -778,6 +945,7 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
 
   // ---- one warp step: VEC voxels per lane at element offset `off` of the instance -----------------
   float coef0 = 0.f;
+  int cur_b = -1;  // instance this warp is accumulating
   auto process = [&](const LT* __restrict__ zb, const TT* __restrict__ tb, const TT* __restrict__ db,
                      LT* __restrict__ gb, auto off) {
     float z[CC][VEC];
@@ -793,12 +961,15 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
       for (int i = 0; i < VEC; ++i) td[i] = t[i];
     }
     float gr[CC][VEC];
-    bool fast = false;
+    // C == 2: non-finite (or absurdly large) logits anywhere in the warp's step -> careful path (poison_nonfinite)
+    bool odd_lane = false;
+    if constexpr (C == 2) odd_lane = lane_suspicious<CC, VEC>(z, nc);
+    bool fast = false, careful = false;
     if constexpr (C == 2 && !DICE) {
       unsigned any = 0u;
 #pragma unroll
       for (int i = 0; i < VEC; ++i) any |= (unsigned)t[i];
-      fast = !__any_sync(__activemask(), any > 1u);
+      fast = !__any_sync(__activemask(), any > 1u || odd_lane);
     }
     if (fast) {
       if constexpr (C == 2 && !DICE) {
@@ -811,12 +982,26 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
         }
       }
     } else {
+      if constexpr (C == 2) {
+        careful = __any_sync(__activemask(), odd_lane);
+        if (careful) poison_nonfinite<CC, VEC, STATS>(z, td, nc, pred_c, tp_c);
+      }
       float nll_c[CC];
       int pred_step[CC];
 #pragma unroll
       for (int c = 0; c < CC; ++c) nll_c[c] = 0.f, pred_step[c] = 0;
 #include "ds_loss_math.inc"
       if (STATS) {
+        if constexpr (C == 2) {
+          if (careful) {
+#pragma unroll
+            for (int c = 0; c < CC; ++c) nll_c[c] = checked_nll(nll_c[c], p.flags + cur_b * 2 + c, nll_limit);
+          }
+        } else {
+          if (sums_suspicious<CC>(nll_c, nc, nll_limit))  // cold: NaN / inf / out-of-range loss sum in this lane's step
+            handle_flagged_step<LT, TT, CC, VEC>(zb, DICE ? db : tb, V, (int64_t)off, nc, nll_c, pred_c, tp_c,
+                                                 p.flags + cur_b * nc, nll_limit);
+        }
         // this lane's fp32 loss sums of the step (fixed voxels, fixed order) become exact integers
         int others = 0;
 #pragma unroll
@@ -850,7 +1035,6 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
   };
 
   // ---- step schedule: group range, interleaved among the group's warps ---------------------------
-  int cur_b = -1;
   if (uniform_inst) {
     // one group per instance (the normal case): the instance is a CTA-uniform value, the base pointers
     // live in uniform registers and a 32-bit voxel offset is all a lane carries from step to step

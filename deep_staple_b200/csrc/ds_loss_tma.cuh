@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
 #pragma unroll
   for (int c = 0; c < CC; ++c) nll_fix[c] = 0, lab_c[c] = 0, pred_c[c] = 0, tp_c[c] = 0;
   const float nll_scale = (float)p.nll_scale;
+  const float nll_limit = (float)(VEC << kNllMeanBits);  // careful path: largest step sum the fixed point takes
   unsigned hist = 0u;
   int hist_steps = 0;
   int n_t1 = 0, n_am1 = 0, n_both = 0, seen_fast = 0;  // fast binary path counters (ds_loss_math_bin.inc)
@@ -239,12 +240,15 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
 #pragma unroll
       for (int i = 0; i < VEC; ++i) td[i] = t[i];
       float gr[CC][VEC];
-      bool fast = false;
+      // C == 2: non-finite (or absurdly large) logits anywhere in the warp's tile row -> careful path (ds_loss.cuh)
+      bool odd_lane = false;
+      if constexpr (C == 2) odd_lane = lane_suspicious<CC, VEC>(z, nc);
+      bool fast = false, careful = false;
       if constexpr (C == 2) {
         unsigned any = 0u;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) any |= (unsigned)t[i];
-        fast = !__any_sync(__activemask(), any > 1u);
+        fast = !__any_sync(__activemask(), any > 1u || odd_lane);
       }
       if (fast) {
         if constexpr (C == 2) {
@@ -255,11 +259,24 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
           seen_fast += VEC;
         }
       } else {
+        if constexpr (C == 2) {
+          careful = __any_sync(__activemask(), odd_lane);
+          if (careful) poison_nonfinite<CC, VEC, true>(z, td, nc, pred_c, tp_c);
+        }
         float nll_c[CC];
         int pred_step[CC];
 #pragma unroll
         for (int c = 0; c < CC; ++c) nll_c[c] = 0.f, pred_step[c] = 0;
 #include "ds_loss_math.inc"
+        if constexpr (C == 2) {
+          if (careful) {
+#pragma unroll
+            for (int c = 0; c < CC; ++c) nll_c[c] = checked_nll(nll_c[c], p.flags + b * 2 + c, nll_limit);
+          }
+        } else {
+          if (sums_suspicious<CC>(nll_c, nc, nll_limit))  // cold: NaN / inf / out-of-range loss sum in this lane's row
+            handle_flagged_step<LT, TT, CC, VEC>(zb, tb, V, v, nc, nll_c, pred_c, tp_c, p.flags + b * nc, nll_limit);
+        }
         int others = 0;
 #pragma unroll
         for (int c = 0; c < CC; ++c) {

@@ -74,6 +74,26 @@ class FusedExchange:
             cls._cache[key] = cls(b_total, num_classes, device, group)
         return cls._cache[key]
 
+    def check(self) -> None:
+        """Raise if this rank ever lost a step (a peer's statistics did not arrive within
+        ``DS_EXCHANGE_TIMEOUT_S`` seconds, default 1800): the kernel then makes every output of that and all
+        later steps NaN -- GradScaler skips them -- because this replica may no longer have applied the same
+        updates as its peers.  One device->host read; call it wherever the training loop already synchronises
+        (``dp_loss.item()``, main_deep_staple.py:775) or once per epoch."""
+        lost_at = int(self.buf[-1].item())
+        if lost_at:
+            raise RuntimeError(
+                f"fused statistics exchange: rank {self.rank} lost step {lost_at} (a peer did not arrive in time); "
+                "all outputs since then are NaN.  Restore the replicas from a checkpoint and call FusedExchange.reset()")
+
+    def reset(self, group=None) -> None:
+        """Collective: clear the exchange buffers (step counter, slots, error word) on every rank."""
+        torch.cuda.synchronize(self.buf.device)
+        dist.barrier(group)
+        self.buf.zero_()
+        torch.cuda.synchronize(self.buf.device)
+        dist.barrier(group)
+
     def next_epoch(self) -> int:
         """Step counter argument of ``ds_dp_loss_fwd_bwd_exchange``: 0 = the kernel keeps the counter in the
         exchange buffer itself (no host state, so the step can be captured in a CUDA graph)."""

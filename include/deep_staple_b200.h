@@ -155,6 +155,15 @@ int ds_consensus_vote_sparse(const int64_t* voxel_index, const int64_t* values, 
  * workspace     ds_dp_loss_workspace_bytes(B_local, C) bytes, 16-byte aligned, ZERO-FILLED once by
  *               the caller before first use (arrival tickets + exact 64-bit integer accumulators;
  *               every launch leaves it all-zero again).
+ *
+ * Non-finite logits behave like torch (main_deep_staple.py:762-768 relies on it: scaler_dp.step() skips the
+ * step when the gradients are not finite): a voxel whose log-softmax is NaN in torch (a NaN logit, a +inf
+ * maximum, all logits -inf) yields NaN for dp_loss, ce_loss, its instance's per_inst_out / NLL statistic, ALL
+ * d_bare_weight (the batch loss couples them) and that voxel's dlogits; a -inf logit of the target class next
+ * to finite ones yields +inf losses, NaN / -inf data-parameter gradients and finite dlogits.  Predicted-class
+ * counts follow torch.argmax (NaN is the maximum).  One deviation: finite logits beyond +-65530 (not
+ * representable in fp16) whose loss sum over one thread's 4-8 voxels exceeds 2^17 per voxel are reported as
+ * +inf (the exact fixed-point accumulation holds a mean loss per voxel of up to 2^17).
  * ------------------------------------------------------------------------------------------- */
 size_t ds_dp_loss_workspace_bytes(int64_t B_local, int64_t C);
 
@@ -177,7 +186,11 @@ int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const void* target, 
  * are those of the GLOBAL batch on every rank.  `epoch` is a step counter that is identical on all ranks and
  * starts at 1; all ranks must make the same sequence of calls.  epoch == 0 uses (and advances) a counter kept in
  * the exchange buffer instead, so that the call has no host-side state and can be captured in a CUDA graph.
- * A peer that does not arrive within 10 s yields NaN losses instead of a hang. */
+ * A peer whose rows do not arrive within DS_EXCHANGE_TIMEOUT_S seconds (environment, default 1800, 0 = wait for
+ * ever) makes the step LOST on this rank: loss_out, d_bare_weight, the missing rows of per_inst_out / inst_stats are
+ * NaN (so a GradScaler skips the step) and the last 8 bytes of this rank's exchange buffer (the error word) hold the
+ * step number; the condition is sticky -- every later step on this rank is NaN too, because its replica may no
+ * longer have made the same updates as its peers -- until the caller zero-fills the buffers again (collectively). */
 size_t ds_dp_loss_exchange_bytes(int64_t B_total, int64_t C, int world);
 
 int ds_dp_loss_fwd_bwd_exchange(const void* logits, int logit_dtype, const void* target, int target_dtype,

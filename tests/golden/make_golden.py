@@ -143,6 +143,87 @@ def make_loss(out):
         out[f"loss__{name}"] = rec
 
 
+def nonfinite_cases():
+    """Non-finite logits: the reference's AMP flow relies on NaN / Inf reaching the loss and the gradients so that
+    ``scaler_dp.step(optimizer_dp)`` skips the step (main_deep_staple.py:762-768).  Each case is a small seeded
+    batch with a few voxels overwritten; ``where`` lists (b, c, flat voxel, value)."""
+    cases = {}
+    inf, nan = np.float32(np.inf), np.float32(np.nan)
+    neg_nan = np.array([0xFFC00000], np.uint32).view(np.float32)[0]  # what x86 inf - inf produces
+
+    def mk(seed, b, c, spatial, dtype, edits, dlogits=True, g=1024.0, use_fixed=True, risk=True):
+        r = rng(seed)
+        logits = (2 * r.standard_normal((b, c, *spatial))).astype(np.float32).astype(dtype)
+        target = r.choice(c, size=(b, *spatial), p=[0.8] + [0.2 / (c - 1)] * (c - 1)).astype(np.uint8)
+        flat = logits.reshape(b, c, -1)
+        tflat = target.reshape(b, -1)
+        for (bi, ci, vi, val, tgt) in edits:
+            flat[bi, ci, vi] = val
+            if tgt is not None:
+                tflat[bi, vi] = tgt
+        m = b + 3
+        emb = r.standard_normal((m, 1)).astype(np.float32)
+        idx = r.permutation(m)[:b].astype(np.int64)
+        fixed = (np.log(r.integers(0, 50000, m).astype(np.float32) + np.float32(np.e)) + np.float32(np.e)).astype(np.float32)
+        cw = (r.random(c) + 0.5).astype(np.float32)
+        return dict(logits=logits, target=target, emb=emb, idx=idx, fixed=fixed, cw=cw, risk=risk, use_fixed=use_fixed,
+                    g=g, dlogits=dlogits)
+
+    f32, f16 = np.float32, np.float16
+    # (instance, class, flat voxel, value, label forced at that voxel)
+    cases["posinf_target"] = mk(40, 3, 2, (4, 8, 8), f32, [(1, 1, 37, inf, 1)])
+    cases["posinf_other"] = mk(41, 3, 2, (4, 8, 8), f32, [(0, 0, 5, inf, 1)])
+    cases["posinf_both"] = mk(42, 2, 2, (4, 8, 8), f32, [(1, 0, 9, inf, 0), (1, 1, 9, inf, 0)])
+    cases["neginf_target"] = mk(43, 3, 2, (4, 8, 8), f32, [(2, 1, 100, -inf, 1)])
+    cases["neginf_other_is_finite"] = mk(44, 3, 2, (4, 8, 8), f32, [(2, 0, 100, -inf, 1), (0, 1, 3, -inf, 0)])
+    cases["neginf_both"] = mk(45, 3, 2, (4, 8, 8), f32, [(0, 0, 64, -inf, 1), (0, 1, 64, -inf, 1)])
+    cases["nan_one_class"] = mk(46, 4, 2, (4, 8, 8), f32, [(3, 1, 255, nan, 0)])
+    cases["negnan_ool"] = mk(47, 4, 2, (4, 8, 8), f32, [(0, 0, 0, neg_nan, 0)], dlogits=False)
+    cases["posinf_ool"] = mk(48, 3, 2, (4, 8, 8), f32, [(1, 1, 17, inf, 0)], dlogits=False)
+    cases["neginf_target_ool"] = mk(49, 3, 2, (4, 8, 8), f32, [(1, 0, 17, -inf, 0)], dlogits=False)
+    cases["fp16_overflow"] = mk(50, 4, 2, (4, 8, 8), f16, [(2, 1, 77, 70000.0, 1), (2, 0, 78, -70000.0, 0)], g=65536.0)
+    cases["fp16_overflow_ool"] = mk(51, 4, 2, (4, 8, 8), f16, [(1, 0, 7, 70000.0, 1)], dlogits=False, g=65536.0)
+    cases["fp16_max_is_finite"] = mk(52, 2, 2, (4, 8, 8), f16, [(1, 0, 7, 65504.0, 1), (1, 1, 7, -65504.0, 1),
+                                                             (0, 1, 8, 65504.0, 1)], g=65536.0)
+    cases["c3_posinf"] = mk(53, 3, 3, (4, 8, 8), f32, [(1, 2, 11, inf, 2)])
+    cases["c3_nan_argmax"] = mk(54, 3, 3, (4, 8, 8), f32, [(1, 1, 11, nan, 0), (2, 2, 5, inf, 0), (0, 0, 3, nan, 1)])
+    cases["c3_neginf_target"] = mk(55, 3, 3, (4, 8, 8), f32, [(0, 1, 200, -inf, 1)])
+    cases["c3_neginf_all"] = mk(56, 3, 3, (4, 8, 8), f32, [(0, 0, 200, -inf, 1), (0, 1, 200, -inf, 1), (0, 2, 200, -inf, 1)])
+    cases["c3_neginf_other_is_finite"] = mk(57, 3, 3, (4, 8, 8), f32, [(0, 0, 20, -inf, 1), (0, 2, 20, -inf, 1)])
+    cases["b1_nan"] = mk(58, 1, 2, (4, 8, 8), f32, [(0, 1, 1, nan, 1)])
+    cases["b1_neginf_target"] = mk(59, 1, 2, (4, 8, 8), f32, [(0, 1, 1, -inf, 1)])
+    cases["odd_shape_nan"] = mk(60, 2, 2, (3, 5, 7), f32, [(1, 0, 104, nan, 0)])
+    cases["huge_finite_f32"] = mk(61, 2, 2, (4, 8, 8), f32, [(0, 1, 5, 3.0e5, 0), (1, 0, 6, -1.0e6, 1)])
+    cases["norisk_nofixed_posinf"] = mk(62, 3, 2, (4, 8, 8), f32, [(1, 1, 37, inf, 1)], use_fixed=False, risk=False)
+    return cases
+
+
+def make_nonfinite(out):
+    for name, c in nonfinite_cases().items():
+        logits = torch.from_numpy(c["logits"])
+        target = torch.from_numpy(c["target"].astype(np.int64))
+        res = ref.reference_loss(
+            logits, target, torch.from_numpy(c["emb"]), torch.from_numpy(c["idx"]),
+            torch.from_numpy(c["fixed"]) if c["use_fixed"] else None,
+            torch.from_numpy(c["cw"]), c["risk"], c["use_fixed"], c["g"], c["dlogits"],
+        )
+        z = logits.float()
+        n_dims = tuple(range(-(z.dim() - 2), 0))  # main_deep_staple.py:513-516
+        rec = dict(
+            logits=c["logits"], target=c["target"], emb=c["emb"], idx=c["idx"], fixed=c["fixed"], cw=c["cw"],
+            risk=np.array(c["risk"]), use_fixed=np.array(c["use_fixed"]), g=np.array(c["g"], np.float64),
+            need_dlogits=np.array(c["dlogits"]),
+            ce_loss=res["ce_loss"].numpy(), dp_loss=res["dp_loss"].numpy(),
+            d_bare_weight=res["d_bare_weight"].numpy(), d_logits_ce=res["d_logits_ce"].numpy(),
+            # main_deep_staple.py:738-739 and :751 on their own, for the per-instance outputs
+            per_inst_ce=torch.nn.CrossEntropyLoss(reduction="none")(z, target).mean(n_dims).numpy(),
+            fg_pred=(z.argmax(1) > 0).sum(dim=n_dims).numpy(),
+        )
+        if c["dlogits"]:
+            rec["d_logits"] = res["d_logits"].numpy()
+        out[f"nonfinite__{name}"] = rec
+
+
 def make_prepass_and_dice(out):
     r = rng(30)
     labels = (r.random((5, 6, 8, 8)) < np.array([0.05, 0.3, 0.0, 0.6, 0.15]).reshape(5, 1, 1, 1)).astype(np.uint8)
@@ -183,6 +264,7 @@ def main():
     out = {}
     make_consensus(out)
     make_loss(out)
+    make_nonfinite(out)
     make_prepass_and_dice(out)
     for name, rec in out.items():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)

@@ -93,6 +93,36 @@ def test_closed_form_gradients_match_reference_autograd(name):
         assert np.abs(dz.numpy() - ref_dz).max() <= tol * np.abs(ref_dz).max()
 
 
+@pytest.mark.parametrize("name", golden_names("nonfinite"))
+def test_nonfinite_oracle_matches_reference_output(name):
+    """NaN / Inf logits (main_deep_staple.py:762-768 relies on them reaching the gradients so that the GradScaler
+    skips the step): the restatement reproduces the reference's NaN / Inf pattern and every finite value."""
+    g = load_golden(name)
+    res = ol.run_loss(
+        torch.from_numpy(g["logits"]), torch.from_numpy(g["target"].astype(np.int64)),
+        torch.from_numpy(g["emb"]), torch.from_numpy(g["idx"]),
+        torch.from_numpy(g["fixed"]) if bool(g["use_fixed"]) else None,
+        torch.from_numpy(g["cw"]), bool(g["risk"]), float(g["g"]), bool(g["need_dlogits"]),
+    )
+    eq = lambda a, b: np.array_equal(a, b, equal_nan=True)
+    assert eq(res.ce_loss.numpy(), g["ce_loss"]) and eq(res.dp_loss.numpy(), g["dp_loss"])
+    assert eq(res.d_bare_weight.numpy(), g["d_bare_weight"])
+    assert eq(res.per_inst_ce.numpy(), g["per_inst_ce"]) and eq(res.fg_pred.numpy(), g["fg_pred"])
+    assert eq(res.d_logits_ce.numpy(), g["d_logits_ce"])
+    if bool(g["need_dlogits"]):
+        assert eq(res.d_logits.numpy(), g["d_logits"])
+    # the closed form of SURVEY.md Appendix A (what the CUDA epilogue evaluates) propagates NaN / Inf identically
+    bare = torch.from_numpy(g["emb"]).reshape(-1)[torch.from_numpy(g["idx"])]
+    fixed_b = torch.from_numpy(g["fixed"])[torch.from_numpy(g["idx"])] if bool(g["use_fixed"]) else None
+    numel = math.prod(g["logits"].shape[2:])
+    loss, grad, _ = ol.closed_form(torch.from_numpy(g["per_inst_ce"]), torch.from_numpy(g["fg_pred"]), bare, fixed_b, numel,
+                                   bool(g["risk"]), float(g["g"]))
+    assert np.isnan(loss.item()) == np.isnan(g["dp_loss"]) and np.isinf(loss.item()) == np.isinf(g["dp_loss"])
+    if g["logits"].shape[0] > 1:  # B == 1: the closed form is 0 x c_b, see the kernel epilogue
+        assert np.array_equal(np.isnan(grad.numpy()), np.isnan(g["d_bare_weight"]))
+        assert np.array_equal(np.isneginf(grad.numpy()), np.isneginf(g["d_bare_weight"]))
+
+
 @pytest.mark.parametrize("name", golden_names("prepass"))
 def test_prepass_oracle_matches_reference_output(name):
     g = load_golden(name)
