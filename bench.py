@@ -3,27 +3,37 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload loss|vote]
 
-Workload (``config.workload``), BASELINE.json configs[1]: the data-parameter-weighted loss, fused
+Default workload (``config.workload``), BASELINE.json configs[1]: the data-parameter-weighted loss, fused
 forward + backward with risk regularisation, fixed weighting, class-weighted CE value and hard-Dice
 statistics, batch 8 x 2 classes x 128^3 per GPU, fp32 logits, int64 labels (the reference's dtypes).
 A step = one pass of the hot path over one batch of synthetic input.
 
-* ``value``      Gvoxel-candidates/s, inputs resident in HBM, the C-ABI call
-                 ``ds_dp_loss_fwd_bwd`` per step (at N > 1 plus the NCCL all-gather of the
-                 per-instance statistics and the replicated epilogue ``ds_dp_loss_finalize``).
-                 Inputs rotate over 3 buffer sets (1.2 GB) so nothing is served from the 126 MB L2.
+* ``value``      Gvoxel-candidates/s, inputs resident in HBM, one C-ABI call per step (``ds_dp_loss_fwd_bwd``;
+                 at N > 1 ``ds_dp_loss_fwd_bwd_exchange``: the per-instance statistics travel inside the kernel
+                 tail over NVLink peer memory).  Inputs rotate over 3 buffer sets (1.2 GB) so nothing is served
+                 from the 126 MB L2.
 * ``roofline``   algorithmic bytes of the fused kernel (24 B per voxel-instance: 2 fp32 logits + one
                  int64 label read, 2 fp32 gradients written) / its average launch duration measured
                  with CUDA events on the launching stream, against MEASURED_PEAKS.json.
 * ``e2e``        the same metric through the public Python API (``dp_weighted_loss`` + backward) with
                  HOST pinned inputs: per step H2D of logits + labels, D2H of the loss and the
-                 data-parameter gradient, copies double-buffered against the kernel.
+                 data-parameter gradient, copies double-buffered against the kernel.  Every rank is bound to
+                 the CPUs / memory of its GPU's NUMA node first (``numa`` key).
+* ``parity_check``  (outside the timed region, every N) the step's outputs against the closed form of the
+                 reference's loss (oracle.dp_loss.closed_form, fp64, host) evaluated on the exchanged
+                 statistics, the statistics of all ranks compared bit for bit, this rank's rows against a plain
+                 single-GPU launch, and the loss sums against stock ATen on the same device.
+* ``configs``    (N = 1) every other BASELINE.json configuration and the AMP variants, kernel only, on this
+                 run's clocks: cfg1 (vote 1 x 10 x 128^3), cfg4 (2D 64 x 2 x 256^2, cold and warm L2),
+                 cfg5 (3 classes, 192 x 160 x 160, fp32 and fp16), cfg2 fp16 forward-only (out-of-line + autocast).
+* ``vote``       BASELINE.json configs[2]: 100 targets x 30 candidates x 128^3 sharded by target over the ranks
+                 (13/12 at N = 8), max-over-ranks time with and without the final gather, strong scaling.
 * ``cpu_baseline``  the oracle (restatement of main_deep_staple.py:716,738-762 on torch CPU) timed on
-                 this box's host cores on a bounded sample (rank 0, N = 1 only).
-* ``--impl reference``  times that same CPU path as the reference arm.
-* ``vote``       (extra key) the consensus weighted vote on a cfg3 shard, with its own roofline.
+                 this box's host cores (rank 0, N = 1 only).
+* ``--impl reference``  times that same CPU path as the reference arm, on the same ``config``.
 
-``--workload vote`` makes the consensus vote (configs[2], sharded by target) the timed workload.
+``--workload vote`` makes the consensus vote (configs[2]) the timed workload: ``value`` = whole-set
+voxel-candidates / max-over-ranks time, ``e2e`` = ``calc_dp_consensus`` from pinned host label volumes.
 """
 from __future__ import annotations
 
@@ -43,11 +53,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "Gvoxel-candidates/s"
+UNIT = "Gvoxel-candidates/s"
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused loss kernel on this workload,
-# from the `ncu --set full` capture summarised in profiles/r01_loss_fwdbwd_ncu_summary.txt
-# (268.5 MB read + 95.95 MB written; the rest of the 134 MB of gradients is still dirty in L2 at kernel end)
+# from the `ncu --set full` capture summarised in profiles/ (268.5 MB read + 95.95 MB written; the rest of
+# the 134 MB of gradients is still dirty in L2 at kernel end)
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 364_468_736
+NCU_TRAFFIC_SOURCE = "profiles/r01_loss_fwdbwd_ncu_summary.txt"
 
 LOSS_CFG = dict(B=8, C=2, S=(128, 128, 128), M=600, grad_scale=65536.0)
 VOTE_CFG = dict(T_global=100, N=30, S=(128, 128, 128))
@@ -64,6 +76,44 @@ def peak_hbm():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# NUMA placement: pinned host buffers and the launching thread next to the GPU
+# ---------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Bind this process to the CPUs of the NUMA node its GPU hangs off (sysfs), BEFORE any pinned allocation:
+    first-touch then places the pinned host buffers on that node, so every rank's H2D traffic stays on its own
+    socket's PCIe root instead of crossing the inter-socket link."""
+    info = {"bound": False}
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        info.update(pci=bus, node=node)
+        cpus = set()
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+                for part in fh.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+        else:  # no NUMA information in sysfs (single-node VM): ask NVML for the GPU's ideal CPU set
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            for w, mask in enumerate(words):
+                cpus.update(64 * w + bit for bit in range(64) if (int(mask) >> bit) & 1)
+            info["source"] = "nvml"
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as e:  # pragma: no cover - depends on the box
+        info["error"] = str(e)[:120]
+    return info
 
 
 # ---------------------------------------------------------------------------------------------
@@ -129,12 +179,18 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # synthetic inputs
 # ---------------------------------------------------------------------------------------------
-def make_loss_inputs(device, seed, cfg=LOSS_CFG, B=None):
+def make_loss_inputs(device, seed, cfg=LOSS_CFG, B=None, dtype=torch.float32, p_fg=(0.05,)):
     B = B or cfg["B"]
     C, S, M = cfg["C"], cfg["S"], cfg["M"]
     gen = torch.Generator(device=device).manual_seed(seed)
-    logits = 2 * torch.randn((B, C, *S), generator=gen, device=device)
-    target = (torch.rand((B, *S), generator=gen, device=device) < 0.05).long()
+    logits = (2 * torch.randn((B, C, *S), generator=gen, device=device)).to(dtype)
+    u = torch.rand((B, *S), generator=gen, device=device)
+    target = torch.zeros((B, *S), dtype=torch.int64, device=device)
+    acc = 0.0
+    for c, p in enumerate(p_fg, start=1):  # class c with probability p_fg[c-1], background otherwise
+        target = torch.where((u >= acc) & (u < acc + p), torch.full_like(target, c), target)
+        acc += p
+    del u
     emb = torch.randn((M,), generator=gen, device=device)
     idx = torch.randperm(M, generator=gen, device=device)[:B]
     gt_num = torch.randint(0, 50000, (M,), generator=gen, device=device).float()
@@ -162,9 +218,12 @@ def ellipsoid_labels(T, N, S, device, seed, dtype):
 # ---------------------------------------------------------------------------------------------
 # the reference arm / cpu baseline: the oracle on host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_loss_baseline(steps, warmup, budget_s=120.0):
-    """Times oracle.dp_loss.run_loss (restatement of main_deep_staple.py:716,738-762, torch CPU, all
-    host threads) on a bounded sample of cfg2.  Returns (Gvox/s, ms/step, cores, sample string)."""
+def cpu_loss_baseline(steps, warmup, budget_s=150.0):
+    """Times oracle.dp_loss.run_loss (restatement of main_deep_staple.py:716,738-762, torch CPU, all host
+    threads).  Each step is the FULL cfg2 batch (8 instances x 2 x 128^3, fwd + backward incl. dlogits) whenever
+    W + K such steps fit the budget; only then is the per-step sample bounded (fewer instances, never fewer
+    than two -- one instance is the degenerate squeeze / zero-gradient path -- then fewer slices).
+    Returns (Gvox/s, ms/step, cores, sample string)."""
     from oracle import dp_loss as ol
 
     cores = os.cpu_count() or 1
@@ -180,20 +239,50 @@ def cpu_loss_baseline(steps, warmup, budget_s=120.0):
                     cfg["grad_scale"], True)
         return time.perf_counter() - t0
 
-    t_probe = run(1, 32) * 4  # one instance, from a quarter-depth probe
+    run(2, 16)  # thread pool / allocator warm-up
+    t_inst = run(2, cfg["S"][0]) / 2  # seconds per full instance, measured on two
     n = max(1, steps + warmup)
-    per_step_budget = budget_s / n
-    B = int(max(1, min(cfg["B"], per_step_budget // max(t_probe, 1e-6))))
-    D = cfg["S"][0]
-    if B == 1 and t_probe > per_step_budget:
-        D = int(max(8, min(cfg["S"][0], cfg["S"][0] * per_step_budget / t_probe)))
+    per_step = budget_s / n
+    B, D = cfg["B"], cfg["S"][0]
+    if t_inst * B > per_step:
+        B = int(max(2, min(cfg["B"], per_step // max(t_inst, 1e-6))))
+        if t_inst * B > per_step:
+            D = int(max(8, min(cfg["S"][0], cfg["S"][0] * per_step / (t_inst * B))))
     for _ in range(warmup):
         run(B, D)
     times = [run(B, D) for _ in range(max(1, steps))]
     vox = B * D * cfg["S"][1] * cfg["S"][2]
     sec = sum(times) / len(times)
-    sample = (f"{B} of {cfg['B']} instances x {cfg['C']} classes x {D}x{cfg['S'][1]}x{cfg['S'][2]} voxels per step, "
-              f"fwd+bwd incl. dlogits, {len(times)} timed steps")
+    whole = B == cfg["B"] and D == cfg["S"][0]
+    sample = (("the full configuration: " if whole else "bounded sample: ") +
+              f"{B} of {cfg['B']} instances x {cfg['C']} classes x {D}x{cfg['S'][1]}x{cfg['S'][2]} voxels per step, "
+              f"fwd+bwd incl. dlogits, {len(times)} timed steps after {warmup} warm-up")
+    return vox / sec / 1e9, sec * 1e3, cores, sample
+
+
+def cpu_vote_baseline(steps, warmup):
+    """oracle.consensus.calc_dp_consensus (= consensus.ipynb:100-109 on torch CPU) on ONE cfg3 target per step."""
+    from oracle import consensus as oc
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = VOTE_CFG
+    labels = ellipsoid_labels(1, c["N"], c["S"], "cpu", 1000, torch.int64)[0]
+    dps = [torch.tensor([float(x)]) for x in 2 * torch.randn(c["N"], generator=torch.Generator().manual_seed(4))]
+    lbls = list(labels)
+
+    def run():
+        t0 = time.perf_counter()
+        oc.calc_dp_consensus(lbls, dps)
+        return time.perf_counter() - t0
+
+    for _ in range(warmup):
+        run()
+    times = [run() for _ in range(max(1, steps))]
+    sec = sum(times) / len(times)
+    vox = c["N"] * labels[0].numel()
+    sample = (f"1 of {c['T_global']} targets x {c['N']} candidates x 128^3 int64 dense per step "
+              f"(calc_dp_consensus), {len(times)} timed steps")
     return vox / sec / 1e9, sec * 1e3, cores, sample
 
 
@@ -201,36 +290,56 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, cores, sample = cpu_loss_baseline(args.steps, args.warmup)
+    if args.workload == "vote":
+        value, ms, cores, sample = cpu_vote_baseline(args.steps, args.warmup)
+        config = vote_config_dict(args.gpus)
+        note = ("reference = torch CPU path of consensus.ipynb:100-109 (oracle port of calc_dp_consensus; the notebook cell "
+                "cannot be imported on the GPU box), all host threads")
+        dtype = "int64"
+    else:
+        value, ms, cores, sample = cpu_loss_baseline(args.steps, args.warmup)
+        config = loss_config_dict(args.gpus)
+        note = ("reference = torch CPU path of main_deep_staple.py:716,738-762 (oracle port; the reference code is "
+                "inline in train_DL and cannot be imported), all host threads")
+        dtype = "f32"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gvoxel-candidates/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": loss_config_dict(1),
-        "cpu_baseline": {"value": value, "unit": "Gvoxel-candidates/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "Gvoxel-candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "note": "reference = torch CPU path of main_deep_staple.py:716,738-762 (oracle port; the reference code is "
-                "inline in train_DL and cannot be imported), all host threads",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "vote" else "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "note": note,
     }
     emit(line)
 
 
-def loss_config_dict(n_gpus, exchange="inside the loss kernel over NVLink peer memory", launch="n/a"):
+def loss_config_dict(n_gpus):
+    """Identical for both arms (ours and --impl reference): the workload, nothing about how it is launched."""
     c = LOSS_CFG
     return {
         "workload": "dp-weighted CE loss fwd+bwd (risk regularisation, fixed weighting, class-weighted CE value, "
                     "hard-Dice statistics), batch 8 x 2 classes x 128^3 per GPU (BASELINE.json configs[1])",
         "batch_per_gpu": c["B"], "global_batch": c["B"] * n_gpus, "classes": c["C"], "volume": list(c["S"]),
         "logits_dtype": "float32", "label_dtype": "int64", "grad_scale": c["grad_scale"],
-        "parallelism": f"dp{n_gpus} (instances sharded; per-instance statistics exchanged {exchange})" if n_gpus > 1 else "single GPU",
+        "parallelism": f"dp{n_gpus} (instances sharded by rank)" if n_gpus > 1 else "single GPU",
         "l2": "inputs rotate over 3 buffer sets of 403 MB (> 126 MB L2); no reuse between steps",
-        "launch": launch,
+    }
+
+
+def vote_config_dict(n_gpus):
+    c = VOTE_CFG
+    return {
+        "workload": "full-set consensus weighted vote: 100 targets x 30 atlas candidates x 128^3, int64 labels, sharded by "
+                    "target over the GPUs (BASELINE.json configs[2])",
+        "targets": c["T_global"], "candidates": c["N"], "volume": list(c["S"]), "label_dtype": "int64",
+        "parallelism": f"targets sharded in contiguous blocks over {n_gpus} GPUs" if n_gpus > 1 else "single GPU",
+        "l2": "every launch streams its whole shard (>= 6.5 GB) once; nothing is reused from the 126 MB L2",
     }
 
 
 # ---------------------------------------------------------------------------------------------
-# our arm
+# our arm: the loss step
 # ---------------------------------------------------------------------------------------------
 class LossStep:
     """Preallocated buffers + the raw C-ABI call of one step (what `value` and `roofline` time)."""
@@ -268,22 +377,29 @@ class LossStep:
 
             self.exchange = FusedExchange.get(self.B_total, self.C, device)
 
-    def kernel(self):
-        b, k = self.b, self.i % len(self.sets)
-        self.i += 1
+    def kernel(self, stats=None, B_total=None, b_offset=None, k=None):
+        b = self.b
+        if k is None:
+            k = self.i % len(self.sets)
+            self.i += 1
         s = self.sets[k]
+        stats = self.stats if stats is None else stats
+        B_total = self.B_total if B_total is None else B_total
+        b_offset = self.rank * self.B if b_offset is None else b_offset
         rc = self.lib.ds_dp_loss_fwd_bwd(
             s["logits"].data_ptr(), b.DS_F32, s["target"].data_ptr(), b.DS_I64, None, self.B, self.C, self.V,
-            self.bare.data_ptr(), self.fixed.data_ptr(), self.B_total, self.rank * self.B, self.cw.data_ptr(), 1,
-            self.scale.data_ptr(), self.dlogits[k].data_ptr(), self.stats.data_ptr(), self.loss_out.data_ptr(),
+            self.bare.data_ptr(), self.fixed.data_ptr(), B_total, b_offset, self.cw.data_ptr(), 1,
+            self.scale.data_ptr(), self.dlogits[k].data_ptr(), stats.data_ptr(), self.loss_out.data_ptr(),
             self.d_bare.data_ptr(), self.per_inst.data_ptr(), self.ws.data_ptr(), self.ws.numel() * 8, self.stream)
         if rc:
             b.check(rc, "ds_dp_loss_fwd_bwd")
 
-    def fused_step(self):
+    def fused_step(self, k=None):
         """data-parallel step as ONE launch: statistics exchange over NVLink peer memory + epilogue in the kernel tail"""
-        b, k, ex = self.b, self.i % len(self.sets), self.exchange
-        self.i += 1
+        b, ex = self.b, self.exchange
+        if k is None:
+            k = self.i % len(self.sets)
+            self.i += 1
         s = self.sets[k]
         rc = self.lib.ds_dp_loss_fwd_bwd_exchange(
             s["logits"].data_ptr(), b.DS_F32, s["target"].data_ptr(), b.DS_I64, None, self.B, self.C, self.V,
@@ -294,11 +410,11 @@ class LossStep:
         if rc:
             b.check(rc, "ds_dp_loss_fwd_bwd_exchange")
 
-    def step(self):
+    def step(self, k=None):
         if self.exchange is not None:
-            self.fused_step()
+            self.fused_step(k)
             return
-        self.kernel()
+        self.kernel(k=k)
         if self.world > 1:
             import torch.distributed as dist
 
@@ -310,6 +426,70 @@ class LossStep:
                 self.per_inst.data_ptr(), self.stream)
             if rc:
                 self.b.check(rc, "ds_dp_loss_finalize")
+
+
+def parity_check(step: LossStep, dist):
+    """One step on buffer set 0, OUTSIDE the timed region, checked four ways (see the module docstring).  The closed
+    form is the reference's loss (main_deep_staple.py:738-762) in fp64 on the host; it is the
+    checker here, never the thing measured."""
+    from oracle import dp_loss as ol
+
+    dev, B, C, V = step.device, step.B, step.C, step.V
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    step.step(k=0)
+    torch.cuda.synchronize()
+    stats = step.stats.clone()
+    loss, ce, d_bare = float(step.loss_out[0]), float(step.loss_out[1]), step.d_bare.clone()
+    out = {}
+    # (1) every rank holds the same global statistics, loss and data-parameter gradients, bit for bit
+    same = True
+    if dist:
+        packed = torch.cat([stats.reshape(-1), d_bare.double(), step.loss_out.double()])
+        allp = torch.empty((step.world, packed.numel()), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allp, packed)
+        same = bool((allp == allp[0:1]).all())
+    out["ranks_bit_identical"] = same
+    # (2) this rank's rows from a plain single-GPU launch over its own instances
+    local = torch.zeros((B, C, 4), dtype=torch.float64, device=dev)
+    keep = (step.loss_out.clone(), step.d_bare.clone(), step.per_inst.clone())
+    step.kernel(stats=local, B_total=B, b_offset=0, k=0)  # reads bare[:B]: only the statistics are compared
+    torch.cuda.synchronize()
+    step.loss_out.copy_(keep[0]), step.d_bare.copy_(keep[1]), step.per_inst.copy_(keep[2])
+    rows_equal = bool(torch.equal(local, stats[step.rank * B:(step.rank + 1) * B]))
+    # (3) the loss sums against stock ATen on this device (fp32 cross_entropy per voxel, summed in fp64)
+    s0 = step.sets[0]
+    nll = torch.nn.functional.cross_entropy(s0["logits"], s0["target"], reduction="none").double().flatten(1)
+    aten = torch.stack([torch.where(s0["target"].flatten(1) == c, nll, torch.zeros_like(nll)).sum(1) for c in range(C)], 1)
+    nll_rel = float(((local[:, :, 0] - aten).abs() / aten.abs().clamp_min(1e-30)).max())
+    fg_equal = bool(torch.equal(local[:, 1:, 2].sum(1), (s0["logits"].argmax(1) > 0).flatten(1).sum(1).double()))
+    del nll, aten
+    flags = torch.tensor([float(rows_equal), float(fg_equal), nll_rel], dtype=torch.float64, device=dev)
+    if dist:
+        mn = flags[:2].clone()
+        mx = flags[2:].clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        rows_equal, fg_equal, nll_rel = bool(mn[0]), bool(mn[1]), float(mx[0])
+    out["stats_equal"] = rows_equal and same
+    out["fg_counts_equal_aten"] = fg_equal
+    out["nll_sums_vs_aten_rel"] = nll_rel
+    # (4) loss and data-parameter gradient of the GLOBAL batch against the closed form on the host
+    st = stats.cpu()
+    per_inst_ce = st[:, :, 0].sum(1) / V
+    fg = st[:, 1:, 2].sum(1)
+    L, grad, _ = ol.closed_form(per_inst_ce, fg, step.bare.cpu(), step.fixed.cpu(), V, True, LOSS_CFG["grad_scale"])
+    cw = step.cw.cpu().double()
+    ce_ref = float((st[:, :, 0] * cw).sum() / (st[:, :, 1] * cw).sum())
+    out["loss_rel"] = abs(loss - float(L)) / abs(float(L))
+    out["ce_rel"] = abs(ce - ce_ref) / abs(ce_ref)
+    out["dbare_rel"] = float((d_bare.cpu().double() - grad).abs().max() / grad.abs().max())
+    out["ok"] = bool(out["stats_equal"] and fg_equal and nll_rel < 1e-5 and out["loss_rel"] < 1e-5 and out["ce_rel"] < 1e-5
+                     and out["dbare_rel"] < 1e-4)
+    out["checked"] = ("global statistics / loss / d_bare_weight identical on all ranks; own rows == single-GPU launch; loss sums "
+                      "vs ATen cross_entropy on device; loss, CE and d_bare_weight vs oracle.dp_loss.closed_form (fp64, host)")
+    return out
 
 
 def timed(fn, steps, warmup, barrier=None):
@@ -379,7 +559,7 @@ def timed_graph(step_obj, fn, steps, warmup, barrier=None):
     return e0.elapsed_time(e1) / 1e3, per_step
 
 
-def e2e_loss(device, steps, warmup):
+def e2e_loss(device, steps, warmup, logits_dtype=torch.float32, label_dtype=torch.int64):
     """Public API with HOST inputs: H2D (pinned) of logits + labels, fused kernel via
     dp_weighted_loss + backward, D2H of loss and data-parameter gradient; copies for step i+1 are
     issued on a second stream while step i computes."""
@@ -387,6 +567,8 @@ def e2e_loss(device, steps, warmup):
 
     c = LOSS_CFG
     host = make_loss_inputs("cpu", 7)
+    host["logits"] = host["logits"].to(logits_dtype)
+    host["target"] = host["target"].to(label_dtype)
     h_logits = [host["logits"].pin_memory(), host["logits"].clone().pin_memory()]
     h_target = [host["target"].pin_memory(), host["target"].clone().pin_memory()]
     d_logits = [torch.empty_like(host["logits"], device=device) for _ in range(2)]
@@ -399,8 +581,9 @@ def e2e_loss(device, steps, warmup):
     main = torch.cuda.current_stream(device)
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
-    h2d = host["logits"].numel() * 4 + host["target"].numel() * 8
+    h2d = host["logits"].numel() * host["logits"].element_size() + host["target"].numel() * host["target"].element_size()
     d2h = h_out.numel() * 4
+    scale = torch.tensor(c["grad_scale"], device=device)
 
     def upload(k):
         with torch.cuda.stream(copy_stream):
@@ -413,8 +596,8 @@ def e2e_loss(device, steps, warmup):
         main.wait_event(ready[k])
         z = d_logits[k].requires_grad_(True)
         bare = bare0.clone().requires_grad_(True)
-        loss = ds.dp_weighted_loss(z, d_target[k], bare, fixed, True, grad_scaler=c["grad_scale"], class_weights=cw)
-        (loss * c["grad_scale"]).backward()
+        loss = ds.dp_weighted_loss(z, d_target[k], bare, fixed, True, grad_scaler=scale, class_weights=cw)
+        (loss * scale).backward()
         h_out[:1].copy_(loss.detach().reshape(1), non_blocking=True)
         h_out[1:].copy_(bare.grad, non_blocking=True)
         z.grad = None
@@ -443,33 +626,244 @@ def e2e_loss(device, steps, warmup):
     return sec, h2d, d2h, float(h_out[0])
 
 
-def vote_section(device, rank, world, steps, warmup, peak):
-    """Consensus vote on this rank's cfg3 shard (targets sharded contiguously; no collective in the
-    timed region).  uint8 labels are the compact opt-in dtype, int64 the reference's."""
+def e2e_vote(device, steps, warmup):
+    """`calc_dp_consensus` (the notebook's call, consensus.ipynb:382-392) on ONE target per step from pinned host
+    label volumes: H2D of the 30 candidate volumes, vote, D2H of the consensus map; uploads double-buffered."""
     import deep_staple_b200 as ds
-    from deep_staple_b200.distributed import shard_range
+
+    c = VOTE_CFG
+    V = c["S"][0] * c["S"][1] * c["S"][2]
+    host = ellipsoid_labels(1, c["N"], c["S"], "cpu", 1000, torch.int64)[0]
+    h_lab = [host.pin_memory(), host.clone().pin_memory()]
+    d_lab = [torch.empty_like(host, device=device) for _ in range(2)]
+    h_out = torch.empty(c["S"], dtype=torch.int64).pin_memory()
+    dps = [float(x) for x in 2 * torch.randn(c["N"], generator=torch.Generator().manual_seed(4))]
+    copy_stream = torch.cuda.Stream(device)
+    main = torch.cuda.current_stream(device)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(k):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[k])
+            d_lab[k].copy_(h_lab[k], non_blocking=True)
+            ready[k].record(copy_stream)
+
+    def compute(k):
+        main.wait_event(ready[k])
+        res = ds.calc_dp_consensus(list(d_lab[k]), dps)
+        h_out.copy_(res, non_blocking=True)
+        freed[k].record(main)
+
+    for k in range(2):
+        freed[k].record(main)
+    n = warmup + steps
+    upload(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = None
+    for i in range(n):
+        if i == warmup:
+            torch.cuda.synchronize()
+            upload(i % 2)
+            e0.record(main)
+            t_start = time.perf_counter()
+        if i + 1 < n and i + 1 != warmup:
+            upload((i + 1) % 2)
+        compute(i % 2)
+    e1.record(main)
+    torch.cuda.synchronize()
+    sec = max(e0.elapsed_time(e1) / 1e3, time.perf_counter() - t_start)
+    return sec, host.numel() * 8, V * 8, c["N"] * V
+
+
+# ---------------------------------------------------------------------------------------------
+# every other BASELINE configuration, kernel only (C ABI), on this run's clocks
+# ---------------------------------------------------------------------------------------------
+class _RawLoss:
+    """Rotating buffer sets + the raw ds_dp_loss_fwd_bwd call for one (B, C, S, dtypes, grad) configuration."""
+
+    def __init__(self, device, B, C, S, ldt, tdt, grad, nsets, p_fg):
+        from deep_staple_b200 import _binding as b
+
+        self.b, self.lib = b, b.load()
+        cfg = dict(B=B, C=C, S=S, M=max(600, B))
+        self.B, self.C, self.V = B, C, math.prod(S)
+        self.sets = []
+        for i in range(nsets):
+            s = make_loss_inputs(device, 50 + i, cfg, dtype=ldt, p_fg=p_fg)
+            self.sets.append((s["logits"], s["target"].to(tdt), torch.empty_like(s["logits"]) if grad else None))
+        gen = torch.Generator(device=device).manual_seed(9)
+        self.bare = torch.randn(B, generator=gen, device=device)
+        self.fixed = torch.rand(B, generator=gen, device=device) * 8 + 3
+        self.cw = torch.ones(C, device=device)
+        self.scale = torch.tensor(65536.0, device=device)
+        self.stats = torch.zeros((B, C, 4), dtype=torch.float64, device=device)
+        self.loss_out = torch.zeros(2, device=device)
+        self.d_bare = torch.zeros(B, device=device)
+        self.per_inst = torch.zeros((B, 4), device=device)
+        self.ws = torch.zeros((int(self.lib.ds_dp_loss_workspace_bytes(B, C)) + 7) // 8, dtype=torch.int64, device=device)
+        self.stream = torch.cuda.current_stream(device).cuda_stream
+        self.ldt, self.tdt = b.logit_dtype(self.sets[0][0]), b.label_dtype(self.sets[0][1])
+        self.i = 0
+
+    def __call__(self):
+        z, t, g = self.sets[self.i % len(self.sets)]
+        self.i += 1
+        rc = self.lib.ds_dp_loss_fwd_bwd(
+            z.data_ptr(), self.ldt, t.data_ptr(), self.tdt, None, self.B, self.C, self.V, self.bare.data_ptr(),
+            self.fixed.data_ptr(), self.B, 0, self.cw.data_ptr(), 1, self.scale.data_ptr(),
+            g.data_ptr() if g is not None else None, self.stats.data_ptr(), self.loss_out.data_ptr(),
+            self.d_bare.data_ptr(), self.per_inst.data_ptr(), self.ws.data_ptr(), self.ws.numel() * 8, self.stream)
+        if rc:
+            self.b.check(rc, "ds_dp_loss_fwd_bwd")
+
+
+def configs_section(device, peak, steps):
+    """BASELINE.json configs[0], [3], [4] and the AMP variants of [1], kernel only through the C ABI, timed with CUDA
+    events both launched one by one from the host ("stream") and replayed from a CUDA graph ("graph")."""
+    import deep_staple_b200 as ds
+
+    out = {}
+
+    def loss_case(key, desc, B, C, S, ldt, tdt, grad, nsets, p_fg, l2):
+        raw = _RawLoss(device, B, C, S, ldt, tdt, grad, nsets, p_fg)
+        n = max(steps // len(raw.sets), 1) * len(raw.sets)
+        t_stream = timed(raw, n, 5) / n
+        t_graph, _ = timed_graph(raw, raw, n, 3)
+        t_graph /= n
+        sl, st = raw.sets[0][0].element_size(), raw.sets[0][1].element_size()
+        alg = B * raw.V * ((2 if grad else 1) * C * sl + st)
+        out[key] = {
+            "workload": desc, "us_stream": t_stream * 1e6, "us_graph": t_graph * 1e6, "algorithmic_bytes": alg,
+            "gbs_graph": alg / t_graph / 1e9, "frac_graph": alg / t_graph / 1e9 / peak,
+            "frac_stream": alg / t_stream / 1e9 / peak, "gvoxel_candidates_per_s": B * raw.V / t_graph / 1e9, "l2": l2,
+        }
+        del raw
+        torch.cuda.empty_cache()
+
+    S3 = (128, 128, 128)
+    f32, f16, i64 = torch.float32, torch.float16, torch.int64
+    loss_case("cfg2_fp16_fwd_bwd", "configs[1] under CUDA autocast (fp16 logits), fwd+bwd", 8, 2, S3, f16, i64, True, 3, (0.05,),
+              "cold: 3 rotating sets, 805 MB")
+    loss_case("cfg2_fp16_fwd_only", "configs[1] out-of-line + autocast (the reference's default step): fp16, forward only",
+              8, 2, S3, f16, i64, False, 4, (0.05,), "cold: 4 rotating sets, 805 MB")
+    loss_case("cfg2_fp32_fwd_only", "configs[1] out-of-line, fp32, forward only", 8, 2, S3, f32, i64, False, 3, (0.05,),
+              "cold: 3 rotating sets, 805 MB")
+    loss_case("cfg4_cold", "configs[3]: 2D slices, batch 64 x 2 x 256x256, fp32, fwd+bwd", 64, 2, (256, 256), f32, i64, True, 8,
+              (0.05,), "cold: 8 rotating sets, 805 MB > 126 MB L2")
+    loss_case("cfg4_warm", "configs[3] again on ONE buffer set (101 MB < L2): warm-L2 figure, labelled as such", 64, 2, (256, 256),
+              f32, i64, True, 1, (0.05,), "warm: the same 101 MB every step")
+    loss_case("cfg4_fp16_cold", "configs[3] under autocast (fp16), fwd+bwd", 64, 2, (256, 256), f16, i64, True, 12, (0.05,),
+              "cold: 12 rotating sets, 805 MB")
+    loss_case("cfg5_fp32", "configs[4] per-GPU throughput variant: 8 x 3 classes x 192x160x160, fp32, fwd+bwd", 8, 3,
+              (192, 160, 160), f32, i64, True, 2, (0.05, 0.01), "cold: 2 rotating sets, 2.5 GB")
+    loss_case("cfg5_fp16", "configs[4] under autocast (fp16), fwd+bwd", 8, 3, (192, 160, 160), f16, i64, True, 2, (0.05, 0.01),
+              "cold: 2 rotating sets, 1.6 GB")
+    loss_case("cfg5_fp16_fwd_only", "configs[4] out-of-line + autocast: fp16, forward only", 8, 3, (192, 160, 160), f16, i64, False,
+              3, (0.05, 0.01), "cold: 3 rotating sets, 1.4 GB")
+    loss_case("cfg5_parity_b1", "configs[4] parity variant: ONE instance per GPU, fp32, fwd+bwd", 1, 3, (192, 160, 160), f32, i64,
+              True, 4, (0.05, 0.01), "cold: 4 rotating sets, 629 MB")
+    # cfg1: the CPU-reference case, 1 target x 10 candidates x 128^3 through the notebook's call and the batched one
+    c = VOTE_CFG
+    V = math.prod(c["S"])
+    nsets = 4
+    labs = [ellipsoid_labels(1, 10, c["S"], device, 77 + i, torch.int64) for i in range(nsets)]
+    dps = 2 * torch.randn((1, 10), generator=torch.Generator(device=device).manual_seed(4), device=device)
+    res = torch.empty((1, *c["S"]), dtype=torch.int64, device=device)
+    st = {"i": 0}
+
+    def vote():
+        st["i"] += 1
+        ds.consensus_batched(labs[st["i"] % nsets], dps, out=res)
+
+    n = max(steps // nsets, 1) * nsets
+    t_stream = timed(vote, n, 5) / n
+    lists = [list(l[0]) for l in labs]
+    dpl = [float(x) for x in dps[0]]
+
+    def vote_api():
+        st["i"] += 1
+        ds.calc_dp_consensus(lists[st["i"] % nsets], dpl)
+
+    t_api = timed(vote_api, max(n // 4, 4), 2) / max(n // 4, 4)
+    alg = V * (10 + 1) * 8
+    out["cfg1_vote"] = {
+        "workload": "configs[0]: consensus vote, 1 target x 10 candidates x 128^3, int64 (ds_consensus_vote)",
+        "us_stream": t_stream * 1e6, "algorithmic_bytes": alg, "frac_stream": alg / t_stream / 1e9 / peak,
+        "gvoxel_candidates_per_s": 10 * V / t_stream / 1e9,
+        "us_calc_dp_consensus": t_api * 1e6,
+        "note": "us_calc_dp_consensus = the notebook's signature (list of 10 dense volumes -> torch.stack copy + vote)",
+        "l2": "cold: 4 rotating label sets, 671 MB",
+    }
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[2]: the full consensus set, sharded by target
+# ---------------------------------------------------------------------------------------------
+def vote_section(device, rank, world, steps, warmup, peak, dist, dtypes=("int64", "uint8")):
+    """100 targets x 30 candidates x 128^3 sharded contiguously by target (consensus.ipynb:382-392 has no
+    dependency between targets).  Per label dtype: the vote alone (no collective; max over ranks of the
+    per-rank CUDA-event time), and `sharded_consensus(gather=True)` (vote + the final all-gather of the label maps,
+    wall clock between barriers, max over ranks)."""
+    import deep_staple_b200 as ds
+    from deep_staple_b200.distributed import shard_range, sharded_consensus
 
     c = VOTE_CFG
     lo, hi = shard_range(c["T_global"], rank, world)
-    T = min(hi - lo, 13)  # 13 targets = the 8-GPU shard; 30 x 128^3 int64 x 13 = 6.5 GB, far beyond L2
-    V = c["S"][0] * c["S"][1] * c["S"][2]
-    out = {}
+    T = hi - lo
+    V = math.prod(c["S"])
+    barrier = (lambda: dist.barrier()) if dist else None
     gen = torch.Generator(device=device).manual_seed(4)
-    dps = 2 * torch.randn((T, c["N"]), generator=gen, device=device)
-    for name, dt, sz in (("int64", torch.int64, 8), ("uint8", torch.uint8, 1)):
-        labels = ellipsoid_labels(T, c["N"], c["S"], device, 1000 + lo, dt)
+    dps_all = 2 * torch.randn((c["T_global"], c["N"]), generator=gen, device=device)
+    dps = dps_all[lo:hi].contiguous()
+    base = torch.cat([ellipsoid_labels(1, c["N"], c["S"], device, 1000 + t, torch.uint8) for t in range(lo, hi)])
+    out = {"targets_global": c["T_global"], "candidates": c["N"], "targets_this_rank": T,
+           "imbalance": (-(-c["T_global"] // world)) / (c["T_global"] / world)}
+    for name in dtypes:
+        dt, sz = (torch.int64, 8) if name == "int64" else (torch.uint8, 1)
+        labels = base.to(dt) if dt != torch.uint8 else base
         res = torch.empty((T, *c["S"]), dtype=dt, device=device)
         fn = lambda: ds.consensus_batched(labels, dps, out=res)
-        sec = timed(fn, steps, warmup)
-        bytes_per_launch = T * V * (c["N"] * sz + sz)
-        out[name] = {
-            "gvoxel_candidates_per_s": T * c["N"] * V * steps / sec / 1e9,
-            "ms_per_launch": sec / steps * 1e3,
-            "targets": T, "candidates": c["N"],
-            "roofline": {"bound": "hbm", "achieved": bytes_per_launch * steps / sec / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": bytes_per_launch * steps / sec / 1e9 / peak},
+        sec = timed(fn, steps, warmup, barrier)
+        own_sec = sec
+        if dist:
+            tmax = torch.tensor([sec], device=device, dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            sec = float(tmax.item())
+        bytes_rank = T * V * (c["N"] * sz + sz)
+        rec = {
+            "ms_vote": sec / steps * 1e3,
+            "gvoxel_candidates_per_s": c["T_global"] * c["N"] * V * steps / sec / 1e9,
+            "roofline_this_rank": {"bound": "hbm", "achieved": bytes_rank * steps / own_sec / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": bytes_rank * steps / own_sec / 1e9 / peak, "algorithmic_bytes": bytes_rank},
+            "timing": "CUDA events around K launches per rank, MAX over ranks; no collective in the region",
         }
+        if dist:
+            gsteps = max(3, min(steps, 10))
+
+            def gathered():
+                sharded_consensus(labels, dps, c["T_global"], gather=True)
+
+            for _ in range(2):
+                gathered()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(gsteps):
+                gathered()
+            torch.cuda.synchronize()
+            dist.barrier()
+            gsec = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+            dist.all_reduce(gsec, op=dist.ReduceOp.MAX)
+            gms = float(gsec.item()) / gsteps * 1e3
+            rec["ms_vote_plus_gather"] = gms
+            rec["ms_gather"] = gms - rec["ms_vote"]
+            rec["gather_bytes_received_per_rank"] = (-(-c["T_global"] // world)) * world * V * sz
+            rec["gvoxel_candidates_per_s_with_gather"] = c["T_global"] * c["N"] * V / (gms / 1e3) / 1e9
+        out[name] = rec
         del labels, res
+        torch.cuda.empty_cache()
     return out
 
 
@@ -492,44 +886,18 @@ def emit(line: dict):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
-def main():
-    quiet_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=40)
-    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--skip-vote", action="store_true")
-    ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--launch", default="graph", choices=["graph", "stream"],
-                    help="timed steps replayed from a CUDA graph (default) or launched one by one from Python")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="N > 1: statistics exchange inside the loss kernel over NVLink peer memory, or NCCL all-gather")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+def max_over_ranks(x, dist, device):
+    if not dist:
+        return x
+    t = torch.tensor([x], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: no CUDA device visible and deep_staple_b200 has no CPU fallback")
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=device)
-    barrier = (lambda: dist.barrier()) if dist else None
-
+def run_loss_workload(args, device, rank, world, local_rank, dist, numa):
     import deep_staple_b200 as ds
 
+    barrier = (lambda: dist.barrier()) if dist else None
     peak, peak_src = peak_hbm()
     step = LossStep(device, 3, rank, world, args.exchange)
     c = LOSS_CFG
@@ -549,12 +917,10 @@ def main():
         sec = timed(step.step, args.steps, 0, barrier)
         launches = ds.launch_count() - launches0
     if dist:
-        dist.barrier()  # nobody leaves the fused-exchange phase while a peer still waits on its flags
-    if dist:
-        tmax = torch.tensor([sec], device=device, dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        sec = float(tmax.item())
-    # the dominant kernel alone (no collective, no epilogue launch): average launch duration
+        dist.barrier()  # nobody leaves the fused-exchange phase while a peer still waits on its rows
+    sec = max_over_ranks(sec, dist, device)
+    parity = None if args.skip_parity else parity_check(step, dist)
+    # the dominant kernel alone (no exchange): average launch duration
     if use_graph:
         ksec, _ = timed_graph(step, step.kernel, args.steps, max(3, args.warmup // 2))
     else:
@@ -563,52 +929,147 @@ def main():
     if not args.skip_e2e:
         del step.sets[1:], step.dlogits[1:]
         torch.cuda.empty_cache()
-        esec, h2d, d2h, _ = e2e_loss(device, args.e2e_steps, 3)
         if dist:
-            tmax = torch.tensor([esec], device=device, dtype=torch.float64)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            esec = float(tmax.item())
-        e2e = {"value": world * vox_per_step * args.e2e_steps / esec / 1e9, "unit": "Gvoxel-candidates/s",
+            dist.barrier()
+        esec, h2d, d2h, _ = e2e_loss(device, args.e2e_steps, 3)
+        esec = max_over_ranks(esec, dist, device)
+        e2e = {"value": world * vox_per_step * args.e2e_steps / esec / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-               "api": "deep_staple_b200.dp_weighted_loss(...) + backward, pinned host inputs, double-buffered copies"}
-    clocks = sampler.stop()
+               "h2d_gbs_per_gpu": h2d * args.e2e_steps / esec / 1e9,
+               "api": "deep_staple_b200.dp_weighted_loss(...) + backward, pinned host inputs (fp32 logits, int64 labels: the "
+                      "reference's dtypes), double-buffered copies"}
+        if world == 1:
+            # the same call with the compact formats the op accepts (autocast fp16 logits, uint8 labels): 8x fewer bytes
+            csec, ch2d, cd2h, _ = e2e_loss(device, args.e2e_steps, 3, torch.float16, torch.uint8)
+            e2e["compact_formats"] = {"value": vox_per_step * args.e2e_steps / csec / 1e9, "unit": UNIT, "logits": "float16",
+                                      "labels": "uint8", "h2d_bytes_per_step": ch2d, "d2h_bytes_per_step": cd2h}
     del step
     torch.cuda.empty_cache()
 
+    configs = None
+    if world == 1 and not args.skip_configs:
+        configs = configs_section(device, peak, 200)
     vote = None
     if not args.skip_vote:
-        vote = vote_section(device, rank, world, max(3, min(args.steps, 20)), 3, peak)
-        if dist:
-            agg = torch.tensor([vote["int64"]["gvoxel_candidates_per_s"], vote["uint8"]["gvoxel_candidates_per_s"]],
-                               device=device, dtype=torch.float64)
-            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-            vote["all_ranks_gvoxel_candidates_per_s"] = {"int64": float(agg[0]), "uint8": float(agg[1])}
+        vote = vote_section(device, rank, world, max(3, min(args.steps, 20)), 3, peak, dist)
+    clocks = sampler.stop()
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         v, ms, cores, sample = cpu_loss_baseline(3, 1, budget_s=25.0)
-        cpu = {"value": v, "unit": "Gvoxel-candidates/s", "cores": cores, "kind": "port", "sample": sample,
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                "ms_per_step": ms, "torch": torch.__version__}
 
     if rank == 0:
         alg_bytes = vox_per_step * (2 * c["C"] * 4 + 8)  # 24 B per voxel-instance
         achieved = alg_bytes * args.steps / ksec / 1e9
         line = {
-            "metric": METRIC, "value": world * vox_per_step * args.steps / sec / 1e9, "unit": "Gvoxel-candidates/s",
+            "metric": METRIC, "value": world * vox_per_step * args.steps / sec / 1e9, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": loss_config_dict(world, "inside the loss kernel over NVLink peer memory" if args.exchange == "fused"
-                                       else "by NCCL all-gather + epilogue launch",
-                                       f"CUDA graph of {graph_chunk(args.steps)} steps, replayed" if use_graph
-                                       else "one C-ABI call per step from the host"),
+            "config": loss_config_dict(world),
+            "launch": (f"CUDA graph of {graph_chunk(args.steps)} steps, replayed" if use_graph
+                       else "one C-ABI call per step from the host"),
+            "exchange": None if world == 1 else ("inside the loss kernel over NVLink peer memory (ds_dp_loss_fwd_bwd_exchange)"
+                                                 if args.exchange == "fused" else "NCCL all-gather + epilogue launch"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_loss_fwdbwd_ncu_summary.txt",
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
                          "kernel": "ds::loss_kernel<float,int64,2,4,true,true>",
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": ksec / args.steps * 1e6,
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "vote": vote,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "numa": numa,
+            "parity_check": parity, "configs": configs, "vote": vote,
         }
         emit(line)
+
+
+def run_vote_workload(args, device, rank, world, local_rank, dist, numa):
+    """--workload vote: BASELINE configs[2] as the timed workload (strong scaling: the set is fixed, ranks share it)."""
+    peak, peak_src = peak_hbm()
+    c = VOTE_CFG
+    V = math.prod(c["S"])
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sec_dtype = vote_section(device, rank, world, args.steps, args.warmup, peak, dist, dtypes=("int64",))
+    rec = sec_dtype["int64"]
+    e2e = None
+    if not args.skip_e2e:
+        esec, h2d, d2h, units = e2e_vote(device, min(args.e2e_steps, 20), 2)
+        esec = max_over_ranks(esec, dist, device)
+        e2e = {"value": world * units * min(args.e2e_steps, 20) / esec / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": min(args.e2e_steps, 20),
+               "api": "deep_staple_b200.calc_dp_consensus(list of 30 volumes, data parameters): one target per step per GPU from "
+                      "pinned host label volumes, consensus map read back"}
+    extra = None
+    if not args.skip_vote:
+        extra = vote_section(device, rank, world, max(3, min(args.steps, 20)), 3, peak, dist, dtypes=("uint8",))
+    clocks = sampler.stop()
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        v, ms, cores, sample = cpu_vote_baseline(5, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms,
+               "torch": torch.__version__}
+    if rank == 0:
+        roof = dict(rec["roofline_this_rank"])
+        roof.update(traffic=None, kernel="ds::vote_kernel<int64,int64>", peak_source=peak_src,
+                    avg_launch_us=roof["algorithmic_bytes"] / roof["achieved"] / 1e3,
+                    note="rank 0's shard; algorithmic bytes = T_r x V x (30 + 1) x 8")
+        line = {
+            "metric": METRIC, "value": rec["gvoxel_candidates_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": rec["ms_vote"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": vote_config_dict(world),
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "numa": numa,
+            "vote": {"int64": rec, **({"uint8": extra["uint8"]} if extra else {}),
+                     **{k: v for k, v in sec_dtype.items() if k != "int64"}},
+        }
+        emit(line)
+
+
+def main():
+    quiet_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="loss", choices=["loss", "vote"],
+                    help="loss: BASELINE configs[1] (default, the metric's configuration); vote: configs[2], the full consensus set")
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-vote", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--launch", default="graph", choices=["graph", "stream"],
+                    help="timed steps replayed from a CUDA graph (default) or launched one by one from Python")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: statistics exchange inside the loss kernel over NVLink peer memory, or NCCL all-gather")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.workload == "vote" and args.steps == ap.get_default("steps"):
+        args.steps = 100  # the default K is sized for the 67 us loss step; a full-set vote takes ~8 ms
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device visible and deep_staple_b200 has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa(local_rank)  # before CUDA context threads and pinned allocations
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    if args.workload == "vote":
+        run_vote_workload(args, device, rank, world, local_rank, dist, numa)
+    else:
+        run_loss_workload(args, device, rank, world, local_rank, dist, numa)
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -153,20 +153,26 @@ def sharded_consensus(
     """Vote on this rank's block of targets (``labels_local [T_r, N, *S]`` = targets
     ``shard_range(n_targets_global, rank, world)``); with ``gather`` every rank receives the full
     ``[T_global, *S]`` stack (one all-gather, the only collective).  Returns ``(maps, near_ties)``."""
-    if vote_fn is None:
-        from .consensus import consensus_batched
-
-        vote_fn = consensus_batched
     rank, world = _world(group)
     lo, hi = shard_range(n_targets_global, rank, world)
     if labels_local.shape[0] != hi - lo:
         raise ValueError(f"rank {rank} owns targets [{lo},{hi}) but got {labels_local.shape[0]} label stacks")
     ties = None
+    # The binary vote only ever emits 0 / 1: with the gather ahead, int64 label stacks are voted into uint8 maps,
+    # which travel 8x lighter through the all-gather (the collective, not the vote, is the expensive part: 1.7 GB
+    # per rank for cfg3 as int64) and are widened back to the labels' dtype on arrival.
+    compact = gather and vote_fn is None and labels_local.dtype == torch.int64
+    if vote_fn is None:
+        from .consensus import consensus_batched
+
+        vote_fn = consensus_batched
     if hi > lo:
-        res = vote_fn(labels_local, data_parameters_local, count_near_ties=count_near_ties)
+        kw = {"out_dtype": torch.uint8} if compact else {}
+        res = vote_fn(labels_local, data_parameters_local, count_near_ties=count_near_ties, **kw)
         local, ties = res if count_near_ties else (res, None)
     else:
-        local = torch.empty((0, *labels_local.shape[2:]), dtype=labels_local.dtype, device=labels_local.device)
+        local = torch.empty((0, *labels_local.shape[2:]), dtype=torch.uint8 if compact else labels_local.dtype,
+                            device=labels_local.device)
     if count_near_ties:
         ties = ties if ties is not None else torch.zeros((), dtype=torch.int64, device=labels_local.device)
         ties = ties.clone()
@@ -175,15 +181,18 @@ def sharded_consensus(
         return local, ties
     # ragged blocks (n_targets % world != 0): pad every block to the largest, gather, cut
     per = -(-n_targets_global // world)
-    padded = torch.zeros((per, *local.shape[1:]), dtype=local.dtype, device=local.device)
-    padded[: local.shape[0]] = local
+    padded = local.contiguous()
+    if local.shape[0] != per:
+        padded = torch.zeros((per, *local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
     full = torch.empty((world * per, *local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(full, padded, group=group)
     parts = []
     for r in range(world):
         a, b = shard_range(n_targets_global, r, world)
         parts.append(full[r * per : r * per + (b - a)])
-    return torch.cat(parts), ties
+    full = torch.cat(parts) if len(parts) > 1 and n_targets_global % world else full[:n_targets_global]
+    return (full.to(labels_local.dtype) if compact else full), ties
 
 
 class _DistributedDPLoss(torch.autograd.Function):

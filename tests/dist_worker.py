@@ -14,12 +14,96 @@ import deep_staple_b200 as ds  # noqa: E402
 from deep_staple_b200 import distributed as dd  # noqa: E402
 
 
+def full_size_case(name, rank, world, dev, B_local, C, shape, dtype=torch.float32, need_dlogits=True):
+    """A BASELINE-sized data-parallel step against the SINGLE-PROCESS CPU ORACLE (oracle.dp_loss.run_loss =
+    main_deep_staple.py:716,738-762 on the gathered global batch), not only against our own 1-GPU kernel:
+    rank 0 generates the global batch and runs the oracle, every rank gets its instances, runs the fused-exchange
+    step and checks loss, ALL global data-parameter gradient rows and its own logits gradient.
+    Tolerances: BASELINE.json north_star (loss 1e-5, gradients 1e-4 relative)."""
+    from oracle import dp_loss as ol
+
+    B = B_local * world
+    V = shape[0] * shape[1] * shape[2]
+    M, g_scale = B + 5, 4096.0
+    gen = torch.Generator().manual_seed(100 + C)
+    emb_w = torch.randn((M, 1), generator=gen)
+    idx = torch.randperm(M, generator=gen)[:B]
+    fixed = torch.rand(M, generator=gen) * 3 + 1
+    cw = torch.rand(C, generator=gen) + 0.5
+    z_local = torch.empty((B_local, C, *shape), dtype=dtype, device=dev)
+    t_local = torch.empty((B_local, *shape), dtype=torch.int64, device=dev)
+    ref_dz = torch.empty((B_local, C, *shape), dtype=dtype, device=dev) if need_dlogits else None
+    scalars = torch.empty(2 + 3 * B, dtype=torch.float64, device=dev)  # dp_loss, ce_loss, d_bare[B], per_inst[B], fg[B]
+    if rank == 0:
+        probs = torch.tensor([0.94, 0.05, 0.01][:C]) if C == 3 else torch.tensor([0.95, 0.05])
+        logits = (2 * torch.randn((B, C, *shape), generator=gen)).to(dtype)
+        target = torch.multinomial(probs, B * V, replacement=True, generator=gen).reshape(B, *shape)
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref = ol.run_loss(logits, target, emb_w, idx, fixed, cw, True, g_scale, need_dlogits)
+        scalars.copy_(torch.cat([ref.dp_loss.reshape(1).double(), ref.ce_loss.reshape(1).double(), ref.d_bare_weight.double(),
+                                 ref.per_inst_ce.double(), ref.fg_pred.double()]))
+        z_parts = [logits[r * B_local:(r + 1) * B_local].contiguous().to(dev) for r in range(world)]
+        t_parts = [target[r * B_local:(r + 1) * B_local].contiguous().to(dev) for r in range(world)]
+        g_parts = [ref.d_logits[r * B_local:(r + 1) * B_local].contiguous().to(dev) for r in range(world)] if need_dlogits else None
+    else:
+        z_parts = t_parts = g_parts = None
+    dist.scatter(z_local, z_parts, src=0)
+    dist.scatter(t_local, t_parts, src=0)
+    if need_dlogits:
+        dist.scatter(ref_dz, g_parts, src=0)
+    dist.broadcast(scalars, src=0)
+    ref_loss, ref_ce = scalars[0], scalars[1]
+    ref_dbare, ref_pi, ref_fg = scalars[2:2 + B], scalars[2 + B:2 + 2 * B], scalars[2 + 2 * B:]
+
+    def rel(a, b):
+        a, b = a.double().reshape(-1), b.double().reshape(-1)
+        return float((a - b).abs().max() / (b.abs().max() + 1e-300))
+
+    sl = slice(rank * B_local, (rank + 1) * B_local)
+    for exchange in ("fused", "nccl"):
+        emb = nn.Embedding(M, 1, sparse=True, _weight=emb_w.clone()).to(dev)
+        z = z_local.clone().requires_grad_(need_dlogits)
+        out = dd.dp_weighted_loss_distributed(z, t_local, emb, idx[sl].to(dev), fixed.to(dev), True, grad_scaler=g_scale,
+                                              class_weights=cw.to(dev), return_all=True, exchange=exchange)
+        (out.dp_loss * g_scale).backward()
+        rows = emb.weight.grad.coalesce().to_dense().reshape(-1)[idx.to(dev)]
+        errs = {"dp_loss": rel(out.dp_loss, ref_loss), "ce_loss": rel(out.ce_loss, ref_ce), "d_bare": rel(rows, ref_dbare),
+                "per_inst_ce": rel(out.per_instance_ce, ref_pi)}
+        fg_equal = bool(torch.equal(out.fg_pred.double(), ref_fg))
+        if need_dlogits:
+            errs["d_logits"] = rel(z.grad.float(), ref_dz.float())
+            # per-instance-normalised: every instance's gradient against ITS OWN magnitude (weights differ by instance)
+            per = (z.grad.float() - ref_dz.float()).abs().flatten(1).amax(1) / ref_dz.float().abs().flatten(1).amax(1)
+            errs["d_logits_per_instance"] = float(per.max())
+        tol_g = 1e-4 if dtype == torch.float32 else 2e-3
+        ok = (errs["dp_loss"] < 1e-5 and errs["ce_loss"] < 1e-5 and errs["d_bare"] < 1e-4 and errs["per_inst_ce"] < 1e-5
+              and fg_equal and errs.get("d_logits", 0.0) < tol_g and errs.get("d_logits_per_instance", 0.0) < tol_g)
+        print(f"[{name}] world {world} rank {rank} B_local {B_local} C {C} shape {tuple(shape)} {str(dtype)[6:]} "
+              f"exchange {exchange}: " + " ".join(f"{k} {v:.2e}" for k, v in errs.items()) + f" fg_equal {fg_equal} "
+              f"-> {'OK' if ok else 'FAIL'}", flush=True)
+        assert ok, (name, exchange, errs, fg_equal)
+    dist.barrier()
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    cases = [a for a in sys.argv[1:] if not a.startswith("-")] or ["small"]
+    if "cfg5" in cases:
+        # BASELINE configs[4] parity variant: 3 classes, 192x160x160, ONE instance per GPU (B_global = world), in-line
+        full_size_case("cfg5-parity", rank, world, dev, 1, 3, (192, 160, 160))
+        full_size_case("cfg5-parity-fp16-ool", rank, world, dev, 1, 3, (192, 160, 160), torch.float16, need_dlogits=False)
+    if "cfg2" in cases:
+        # BASELINE configs[1] per GPU: 8 instances x 2 classes x 128^3
+        full_size_case("cfg2-dp", rank, world, dev, 8, 2, (128, 128, 128))
+    if "small" not in cases:
+        if rank == 0:
+            print("DIST_OK", world)
+        dist.destroy_process_group()
+        return
 
     # ---- data-parallel loss (cfg5 shape class: 3 classes) -------------------------------------------
     gen = torch.Generator().manual_seed(0)
