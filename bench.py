@@ -449,7 +449,13 @@ def parity_check(step: LossStep, dist):
         packed = torch.cat([stats.reshape(-1), d_bare.double(), step.loss_out.double()])
         allp = torch.empty((step.world, packed.numel()), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allp, packed)
-        same = bool((allp == allp[0:1]).all())
+        eq = (allp == allp[0:1]).all(0)
+        n_st = stats.numel()
+        parts = {"stats": bool(eq[:n_st].all()), "d_bare_weight": bool(eq[n_st:n_st + d_bare.numel()].all()),
+                 "dp_loss": bool(eq[-2]), "ce_loss": bool(eq[-1])}
+        same = all(parts.values())
+        if not same:
+            out["ranks_differ_in"] = [k for k, v in parts.items() if not v]
     out["ranks_bit_identical"] = same
     # (2) this rank's rows from a plain single-GPU launch over its own instances
     local = torch.zeros((B, C, 4), dtype=torch.float64, device=dev)

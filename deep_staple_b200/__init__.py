@@ -22,7 +22,7 @@ from .loss import (  # noqa: F401
     weighted_ce,
 )
 from .metrics import dice_from_label_maps, dice_from_stats, prepass_constants  # noqa: F401
-from .optim import dp_optimizer_step  # noqa: F401
+from .optim import LossSection, dp_optimizer_step  # noqa: F401
 from .snapshot import build_snapshot, load_snapshot, save_snapshot  # noqa: F401
 from . import distributed  # noqa: F401,E402
 

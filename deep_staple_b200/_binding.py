@@ -41,6 +41,9 @@ SIGNATURES = {
     "ds_dp_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                    c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ds_dp_loss_fwd_bwd_indexed": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ds_dp_loss_exchange_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "ds_dp_loss_fwd_bwd_exchange": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64,
                                             c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p,
@@ -54,8 +57,13 @@ SIGNATURES = {
     "ds_dp_loss_backward_logits": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p,
                                            c_int64, c_void_p, c_void_p, c_void_p]),
     "ds_rescale_inplace": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "ds_dp_loss_backward_reconcile": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                              c_void_p]),
     "ds_sparse_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                                     c_double, c_double, c_double, c_double, c_void_p]),
+    "ds_sparse_adam_scaler_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_double, c_double,
+                                           c_double, c_int, c_void_p]),
     "ds_label_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                c_size_t, c_void_p]),
 }
@@ -105,7 +113,8 @@ def ptr(t) -> int | None:
 
 
 def stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw handle of the caller's current stream on `device` (no Stream object is built: ~0.3 us instead of ~3)."""
+    return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
 
 
 def logit_dtype(t: torch.Tensor) -> int:

@@ -168,6 +168,21 @@ __global__ void __launch_bounds__(kThreads) rescale_kernel(T* __restrict__ x, in
     x[i] = Logit<T>::from_f32(Logit<T>::to_f32(x[i]) * r);
 }
 
+// backward of the fused loss in ONE launch: the data-parameter gradient handed to autograd and -- only if the
+// gradient that arrived differs from the scale assumed in the fused pass -- the rescale of the stored dlogits
+template <typename T>
+__global__ void __launch_bounds__(kThreads) reconcile_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ d_in,
+                                                             float* __restrict__ d_out, int64_t B,
+                                                             const float* __restrict__ numer, const float* __restrict__ denom) {
+  const float a = __ldg(numer), b = denom ? __ldg(denom) : 1.0f;
+  const float r = __fdiv_rn(a, b);  // same fp32 operations as torch's (g / assumed) * d_bare
+  if (blockIdx.x == 0)
+    for (int64_t i = threadIdx.x; i < B; i += kThreads) d_out[i] = __fmul_rn(__ldg(d_in + i), r);
+  if (x == nullptr || a == b) return;  // the GradScaler flow: nothing to rescale, nothing read
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = Logit<T>::from_f32(Logit<T>::to_f32(x[i]) * r);
+}
+
 // label maps only: per instance and class  #(target==c), #(pred==c), #(pred==c && target==c).
 // Same persistent warp-tile schedule and exact integer accumulation as the loss kernel.
 // CT: compile-time class count (2, 3, 4) or 0 = run-time value <= DS_MAX_CLASSES.  The generic form spends ~100
@@ -238,7 +253,7 @@ int dp_loss_fwd_bwd_impl(const char* who, const void* logits, int logit_dtype, c
                          const float* grad_scale, void* dlogits, double* inst_stats, float* loss_out,
                          float* d_bare_weight, float* per_inst_out, const unsigned long long* peer_bases, int rank,
                          int world, unsigned long long epoch, void* workspace, size_t workspace_bytes,
-                         ds_stream_t stream) {
+                         ds_stream_t stream, const int64_t* gather_idx = nullptr) {
   if (int rc = check_common(who, logits, logit_dtype, target, target_dtype, B_local, C, V)) return rc;
   if (!bare_weight) return fail(DS_ERR_NULL, "%s: bare_weight is required", who);
   if (!peer_bases && !inst_stats) return fail(DS_ERR_NULL, "%s: inst_stats is required", who);
@@ -253,6 +268,7 @@ int dp_loss_fwd_bwd_impl(const char* who, const void* logits, int logit_dtype, c
   LossParams p{};
   p.logits = logits, p.target = target, p.dice_target = dice_target, p.dlogits = dlogits;
   p.bare_weight = bare_weight, p.fixed_w = fixed_w, p.class_w = class_w, p.grad_scale = grad_scale;
+  p.gather_idx = gather_idx;
   p.inst_stats = inst_stats, p.loss_out = loss_out, p.d_bare_weight = d_bare_weight, p.per_inst_out = per_inst_out;
   p.B_local = B_local, p.B_total = B_total, p.b_offset = b_offset, p.V = V, p.C = (int)C;
   p.use_risk = use_risk ? 1 : 0, p.mode = kModeDP, p.finalize = (whole || peer_bases) ? 1 : 0, p.dp_outputs = 1;
@@ -278,6 +294,18 @@ extern "C" int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const voi
                               V, bare_weight, fixed_w, B_total, b_offset, class_w, use_risk, grad_scale, dlogits,
                               inst_stats, loss_out, d_bare_weight, per_inst_out, nullptr, 0, 1, 0, workspace,
                               workspace_bytes, stream);
+}
+
+extern "C" int ds_dp_loss_fwd_bwd_indexed(const void* logits, int logit_dtype, const void* target, int target_dtype,
+                                          const void* dice_target, int64_t B, int64_t C, int64_t V, const float* dp_table,
+                                          const float* fixed_table, const int64_t* idx, const float* class_w, int use_risk,
+                                          const float* grad_scale, void* dlogits, double* inst_stats, float* loss_out,
+                                          float* d_bare_weight, float* per_inst_out, void* workspace,
+                                          size_t workspace_bytes, ds_stream_t stream) {
+  if (!idx) return fail(DS_ERR_NULL, "ds_dp_loss_fwd_bwd_indexed: idx is required");
+  return dp_loss_fwd_bwd_impl("ds_dp_loss_fwd_bwd_indexed", logits, logit_dtype, target, target_dtype, dice_target, B, C, V,
+                              dp_table, fixed_table, B, 0, class_w, use_risk, grad_scale, dlogits, inst_stats, loss_out,
+                              d_bare_weight, per_inst_out, nullptr, 0, 1, 0, workspace, workspace_bytes, stream, idx);
 }
 
 extern "C" size_t ds_dp_loss_exchange_bytes(int64_t B_total, int64_t C, int world) {
@@ -373,6 +401,33 @@ extern "C" int ds_rescale_inplace(void* x, int dtype, int64_t n, const float* nu
     case DS_F16: rescale_kernel<__half><<<(unsigned)blocks, kThreads, 0, s>>>((__half*)x, n, numer, denom); break;
     case DS_BF16:
       rescale_kernel<__nv_bfloat16><<<(unsigned)blocks, kThreads, 0, s>>>((__nv_bfloat16*)x, n, numer, denom);
+      break;
+    default: return fail(DS_ERR_DTYPE, "%s: dtype must be DS_F32, DS_F16 or DS_BF16", who);
+  }
+  count_launch();
+  return check_launch(who);
+}
+
+extern "C" int ds_dp_loss_backward_reconcile(void* dlogits, int dtype, int64_t n, const float* d_bare_in, float* d_bare_out,
+                                             int64_t B, const float* grad_out, const float* assumed, ds_stream_t stream) {
+  const char* who = "ds_dp_loss_backward_reconcile";
+  if (!d_bare_in || !d_bare_out || !grad_out) return fail(DS_ERR_NULL, "%s: d_bare_in, d_bare_out and grad_out are required", who);
+  if (B <= 0 || (dlogits && n <= 0)) return fail(DS_ERR_SHAPE, "%s: B and n must be positive", who);
+  if (int rc = ds_device_check()) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int64_t blocks = dlogits ? (n + kThreads * 8 - 1) / (kThreads * 8) : 1;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  switch (dlogits ? dtype : DS_F32) {
+    case DS_F32:
+      reconcile_kernel<float><<<(unsigned)blocks, kThreads, 0, s>>>((float*)dlogits, n, d_bare_in, d_bare_out, B, grad_out, assumed);
+      break;
+    case DS_F16:
+      reconcile_kernel<__half><<<(unsigned)blocks, kThreads, 0, s>>>((__half*)dlogits, n, d_bare_in, d_bare_out, B, grad_out, assumed);
+      break;
+    case DS_BF16:
+      reconcile_kernel<__nv_bfloat16><<<(unsigned)blocks, kThreads, 0, s>>>((__nv_bfloat16*)dlogits, n, d_bare_in, d_bare_out, B,
+                                                                         grad_out, assumed);
       break;
     default: return fail(DS_ERR_DTYPE, "%s: dtype must be DS_F32, DS_F16 or DS_BF16", who);
   }

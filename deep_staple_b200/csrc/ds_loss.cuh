@@ -58,6 +58,8 @@ struct LossParams {
   void* dlogits;
   const float* bare_weight;     // [B_total] (kModeDP) or inst_weight (kModeBwd)
   const float* fixed_w;         // [B_total] or null
+  const int64_t* gather_idx;    // null, or [B_total] rows of the batch: bare_weight / fixed_w are then the full [M] tables
+                                // (embedding.weight, fixed_weighting) and instance b reads row gather_idx[b] (:741, :748)
   const float* class_w;         // [C] or null
   const double* class_counts;   // [C] (kModeCE)
   const float* grad_scale;      // device scalar or null
@@ -107,6 +109,13 @@ __device__ __forceinline__ void dbg_stamp(int slot) {
 #define DS_STAMP(slot)
 #endif
 
+// data parameter / fixed weight of instance i of the global batch: direct, or drawn from the tables by dataset index
+__device__ __forceinline__ float dp_at(const LossParams& p, int64_t i) {
+  return __ldg(p.bare_weight + (p.gather_idx ? __ldg(p.gather_idx + i) : i));
+}
+__device__ __forceinline__ float fw_at(const LossParams& p, int64_t i) {
+  return __ldg(p.fixed_w + (p.gather_idx ? __ldg(p.gather_idx + i) : i));
+}
 // sigmoid of a data parameter (:743): fp32 like the reference, widened for the batch sums
 __device__ __forceinline__ double sigmoid_d(float x) { return (double)(1.0f / (1.0f + expf(-x))); }
 
@@ -304,11 +313,11 @@ __device__ __forceinline__ float batch_mean_sigmoid(const LossParams& p, double*
   const int lane = threadIdx.x & 31;
   if (p.B_total <= 64) {
     float s = 0.f;
-    for (int i = lane; i < (int)p.B_total; i += 32) s += sigmoid_f(__ldg(p.bare_weight + i));
+    for (int i = lane; i < (int)p.B_total; i += 32) s += sigmoid_f(dp_at(p, i));
     return warp_sum(s) / (float)p.B_total;
   }
   double ssum = 0.0;
-  for (int64_t i = threadIdx.x; i < p.B_total; i += kThreads) ssum += (double)sigmoid_f(__ldg(p.bare_weight + i));
+  for (int64_t i = threadIdx.x; i < p.B_total; i += kThreads) ssum += (double)sigmoid_f(dp_at(p, i));
   return (float)(block_sum(ssum, scratch) / (double)p.B_total);
 }
 
@@ -325,8 +334,8 @@ __device__ __forceinline__ InstTerms inst_terms(const LossParams& p, int64_t b) 
     if (c > 0) t.fg += load_stat(p, st + c * kStatsPerClass + DS_STAT_PRED);
   }
   const double V = (double)p.V;
-  t.f = p.fixed_w ? (double)__ldg(p.fixed_w + b) : 1.0;
-  t.s = sigmoid_d(__ldg(p.bare_weight + b));
+  t.f = p.fixed_w ? (double)fw_at(p, b) : 1.0;
+  t.s = sigmoid_d(dp_at(p, b));
   t.cb = (t.nll / V - (p.use_risk ? t.fg / V : 0.0)) / t.f;  // (l_b - n_b / V) / f_b
   return t;
 }
@@ -381,8 +390,8 @@ __device__ __forceinline__ bool epi_two_phase(const LossParams& p) { return p.B_
 __device__ __forceinline__ void epi_fill(const LossParams& p, EpiShared& e) {
   const int i = threadIdx.x;
   if (i < (int)p.B_total) {
-    e.s[i] = p.dp_outputs ? sigmoid_f(__ldg(p.bare_weight + i)) : 1.f;
-    e.f[i] = (p.dp_outputs && p.fixed_w) ? __ldg(p.fixed_w + i) : 1.f;
+    e.s[i] = p.dp_outputs ? sigmoid_f(dp_at(p, i)) : 1.f;
+    e.f[i] = (p.dp_outputs && p.fixed_w) ? fw_at(p, i) : 1.f;
   }
   if (i < p.C) e.cw[i] = p.class_w ? __ldg(p.class_w + i) : 0.f;
 }
@@ -401,10 +410,10 @@ __device__ __forceinline__ DpPrologue dp_prologue(const LossParams& p, EpiShared
   const int lane = threadIdx.x & 31, B = (int)p.B_total;
   if (B <= 64) {
     const bool on0 = lane < B, on1 = lane + 32 < B;
-    const float x0 = on0 ? __ldg(p.bare_weight + lane) : 0.f;
-    const float x1 = on1 ? __ldg(p.bare_weight + lane + 32) : 0.f;
-    const float f0 = (on0 && p.fixed_w) ? __ldg(p.fixed_w + lane) : 1.f;
-    const float f1 = (on1 && p.fixed_w) ? __ldg(p.fixed_w + lane + 32) : 1.f;
+    const float x0 = on0 ? dp_at(p, lane) : 0.f;
+    const float x1 = on1 ? dp_at(p, lane + 32) : 0.f;
+    const float f0 = (on0 && p.fixed_w) ? fw_at(p, lane) : 1.f;
+    const float f1 = (on1 && p.fixed_w) ? fw_at(p, lane + 32) : 1.f;
     const float s0 = on0 ? sigmoid_f(x0) : 0.f, s1 = on1 ? sigmoid_f(x1) : 0.f;
     r.mean_s = warp_sum(s0 + s1) / (float)B;
     if (fill && threadIdx.x < 32) {
@@ -911,8 +920,8 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     if (!GRAD || p.mode == kModeCE) return 0.f;
     if (p.mode == kModeBwd) return gV * __ldg(p.bare_weight + b * p.weight_stride);
     const int64_t bg = p.b_offset + b;
-    const float f = p.fixed_w ? __ldg(p.fixed_w + bg) : 1.0f;
-    return gV * sigmoid_f(__ldg(p.bare_weight + bg)) / (mean_s * f);
+    const float f = p.fixed_w ? fw_at(p, bg) : 1.0f;
+    return gV * sigmoid_f(dp_at(p, bg)) / (mean_s * f);
   };
 
   // C == 2 without a separate Dice target: all label / true-positive counts come from one packed

@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
       coef0 = home.coef_home;
       if (GRAD && !home.have_home) {  // batches of more than 64 instances
         const int64_t bg = p.b_offset + b;
-        const float f = p.fixed_w ? __ldg(p.fixed_w + bg) : 1.0f;
-        coef0 = gV * sigmoid_f(__ldg(p.bare_weight + bg)) / (home.mean_s * f);
+        const float f = p.fixed_w ? fw_at(p, bg) : 1.0f;
+        coef0 = gV * sigmoid_f(dp_at(p, bg)) / (home.mean_s * f);
       }
     }
   } else {

@@ -209,6 +209,9 @@ class _DistributedDPLoss(torch.autograd.Function):
         fixed = None if fixed_global is None else fixed_global.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
         cw = None if class_w is None else class_w.detach().to(device=dev, dtype=torch.float32).contiguous()
         need_dlogits = ctx.needs_input_grad[0]
+        if need_dlogits and scale is None and z.dtype is not torch.float32:
+            raise ValueError("half-precision dp_logits that require grad need grad_scaler=...: their gradient is written by "
+                             "the fused pass already scaled (unscaled it would underflow fp16)")
         dlogits = torch.empty_like(z) if need_dlogits else None
         stats = torch.zeros((B_total, C, _b.DS_STATS), dtype=torch.float64, device=dev)
         loss_out = torch.empty(2, dtype=torch.float32, device=dev)
@@ -243,7 +246,8 @@ class _DistributedDPLoss(torch.autograd.Function):
                         _b.ptr(scale), _b.ptr(loss_out), _b.ptr(d_bare), _b.ptr(per_inst), _b.stream_ptr(dev),
                     )
                     _b.check(rc, "ds_dp_loss_finalize")
-        ctx.assumed = scale
+        ctx.assumed = scale          # scale inside d_bare (never rewritten)
+        ctx.dlogits_scale = scale    # scale inside the stored dlogits (rewritten by a reconciling backward)
         ctx.bare_shape = bare_global.shape
         ctx.logits_shape = dp_logits.shape
         ctx.save_for_backward(d_bare, dlogits)
@@ -254,19 +258,31 @@ class _DistributedDPLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, _a, _b2, _c):
         d_bare, dlogits = ctx.saved_tensors
-        g = grad_loss.detach().to(torch.float32).reshape(())
-        ratio = g if ctx.assumed is None else g / ctx.assumed
-        grad_bare = (d_bare * ratio).reshape(ctx.bare_shape)
+        dev = d_bare.device
+        g = grad_loss
+        if g.dtype is not torch.float32 or g.dim() != 0 or g.requires_grad:
+            g = g.detach().to(torch.float32).reshape(())
+        grad_bare = torch.empty_like(d_bare)
+        lib = _b.load()
+        with torch.cuda.device(dev):
+            fused = dlogits
+            if dlogits is not None and ctx.dlogits_scale is not ctx.assumed:  # a second backward after a reconciling one
+                one = ctx.dlogits_scale if ctx.dlogits_scale is not None else torch.ones((), dtype=torch.float32, device=dev)
+                rc = lib.ds_rescale_inplace(_b.ptr(dlogits), _b.logit_dtype(dlogits), dlogits.numel(), _b.ptr(g), _b.ptr(one),
+                                            _b.stream_ptr(dev))
+                _b.check(rc, "ds_rescale_inplace")
+                fused = None
+            # one launch: d_bare x (g / assumed) into a fresh tensor, and the stored dlogits rescaled only if g differs
+            rc = lib.ds_dp_loss_backward_reconcile(
+                _b.ptr(fused), _b.logit_dtype(fused) if fused is not None else _b.DS_F32,
+                fused.numel() if fused is not None else 0, _b.ptr(d_bare), _b.ptr(grad_bare), d_bare.numel(), _b.ptr(g),
+                _b.ptr(ctx.assumed), _b.stream_ptr(dev))
+            _b.check(rc, "ds_dp_loss_backward_reconcile")
         grad_logits = None
         if dlogits is not None:
-            one = ctx.assumed if ctx.assumed is not None else torch.ones((), dtype=torch.float32, device=g.device)
-            lib = _b.load()
-            with torch.cuda.device(dlogits.device):
-                rc = lib.ds_rescale_inplace(_b.ptr(dlogits), _b.logit_dtype(dlogits), dlogits.numel(), _b.ptr(g),
-                                            _b.ptr(one), _b.stream_ptr(dlogits.device))
-            _b.check(rc, "ds_rescale_inplace")
+            ctx.dlogits_scale = g
             grad_logits = dlogits.view(ctx.logits_shape)
-        return grad_logits, grad_bare, None, None, None, None, None, None, None, None
+        return grad_logits, grad_bare.reshape(ctx.bare_shape), None, None, None, None, None, None, None, None
 
 
 def dp_weighted_loss_distributed(

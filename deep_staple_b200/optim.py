@@ -12,7 +12,7 @@ import torch
 
 from . import _binding as _b
 
-__all__ = ["dp_optimizer_step"]
+__all__ = ["dp_optimizer_step", "LossSection"]
 
 
 def dp_optimizer_step(
@@ -89,3 +89,109 @@ def dp_optimizer_step(
     else:
         state["step"] = step
     return applied
+
+
+class LossSection:
+    """The out-of-line data-parameter step of the reference's training loop (``use_ool_dp_loss=True``, its
+    default; main_deep_staple.py:738-773) as TWO kernel launches and nothing else:
+
+        dp_loss value + its gradient w.r.t. the drawn data parameters     (:738-759, :762)   ds_dp_loss_fwd_bwd_indexed
+        scaler_dp.step(optimizer_dp); scaler_dp.update()                  (:764-768)         ds_sparse_adam_scaler_step
+
+    No autograd graph, no ``embedding(idx)`` / ``fixed_weighting[idx]`` gathers (the kernel draws both by dataset
+    index), no sparse gradient tensor, no host synchronisation -- the host cost of a call is two ctypes calls, and
+    because nothing depends on host state the call can be captured in a CUDA graph when its inputs are static.
+    torch's objects stay the owners of all state: ``embedding.weight``, ``optimizer_dp.state`` (moments; the step
+    counter is mirrored on the device and written back by ``sync()`` and automatically before
+    ``optimizer_dp.state_dict()``), ``scaler_dp`` (its ``_scale`` / ``_growth_tracker`` tensors are updated in place),
+    so checkpoints (torch_utils.py:354-360) are unchanged.
+
+        section = ds.LossSection(embedding, optimizer_dp, scaler_dp, fixed_weighting=fixed_weighting)
+        dp_loss = section(dp_logits, b_seg_modified, b_idxs_dataset)        # replaces :738-768 in the OOL branch
+    """
+
+    def __init__(self, embedding: torch.nn.Embedding, optimizer_dp: torch.optim.SparseAdam, scaler_dp=None, *,
+                 fixed_weighting: Optional[torch.Tensor] = None, use_risk_regularization: bool = True,
+                 class_weights: Optional[torch.Tensor] = None):
+        w = embedding.weight
+        _b.require_cuda(w, "embedding.weight")
+        if w.dim() != 2 or w.shape[1] != 1 or w.dtype != torch.float32 or not w.is_contiguous():
+            raise ValueError("the data-parameter embedding must be a contiguous float32 [M, 1] table")
+        self.embedding, self.optimizer, self.scaler = embedding, optimizer_dp, scaler_dp
+        self.group = next(g for g in optimizer_dp.param_groups if any(p is w for p in g["params"]))
+        if self.group.get("maximize", False):
+            raise ValueError("maximize=True is not supported")
+        dev = w.device
+        self.device = dev
+        state = optimizer_dp.state[w]
+        if len(state) == 0:  # same lazy initialisation as SparseAdam.step
+            state["step"] = 0
+            state["exp_avg"] = torch.zeros_like(w, memory_format=torch.preserve_format)
+            state["exp_avg_sq"] = torch.zeros_like(w, memory_format=torch.preserve_format)
+        self.state = state
+        self.step_count = torch.tensor([int(state["step"])], dtype=torch.int64, device=dev)
+        self.found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.fixed = None
+        if fixed_weighting is not None:
+            self.fixed = fixed_weighting.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+            if self.fixed.numel() != w.shape[0]:
+                raise ValueError("fixed_weighting must have one entry per embedding row")
+        self.cw = None if class_weights is None else class_weights.detach().to(device=dev, dtype=torch.float32).contiguous()
+        self.use_risk = 1 if use_risk_regularization else 0
+        self.scale = self.tracker = None
+        self.growth = (2.0, 0.5, 2000)
+        if scaler_dp is not None and scaler_dp.is_enabled():
+            # private GradScaler state: fail loudly if a torch upgrade renames it instead of silently mis-scaling
+            for attr in ("_scale", "_growth_tracker", "_lazy_init_scale_growth_tracker", "get_growth_factor",
+                         "get_backoff_factor", "get_growth_interval"):
+                if not hasattr(scaler_dp, attr):
+                    raise RuntimeError(f"torch.amp.GradScaler has no attribute {attr!r}: unsupported torch version")
+            if scaler_dp._scale is None:
+                scaler_dp._lazy_init_scale_growth_tracker(dev)
+            self.scale, self.tracker = scaler_dp._scale, scaler_dp._growth_tracker
+            if self.scale.dtype != torch.float32 or self.tracker.dtype != torch.int32:
+                raise RuntimeError("unexpected GradScaler tensor dtypes: unsupported torch version")
+            self.growth = (float(scaler_dp.get_growth_factor()), float(scaler_dp.get_backoff_factor()),
+                           int(scaler_dp.get_growth_interval()))
+        if hasattr(optimizer_dp, "register_state_dict_pre_hook"):
+            optimizer_dp.register_state_dict_pre_hook(lambda opt: self.sync())
+        self._lib = _b.load()
+
+    def sync(self) -> int:
+        """Write the device-side step counter back into ``optimizer_dp.state`` (one device->host read)."""
+        self.state["step"] = int(self.step_count.item())
+        return self.state["step"]
+
+    def __call__(self, dp_logits: torch.Tensor, b_seg_modified: torch.Tensor, b_idxs_dataset: torch.Tensor,
+                 *, dice_target: Optional[torch.Tensor] = None, return_all: bool = False):
+        from . import loss as _l
+
+        z, t, B, C, V = _l._flat_inputs(dp_logits, b_seg_modified)
+        dev = self.device
+        idx = b_idxs_dataset
+        if idx.dtype is not torch.int64 or idx.device != dev or idx.dim() != 1 or not idx.is_contiguous():
+            idx = idx.detach().to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        if idx.shape[0] != B:
+            raise ValueError(f"{B} instances in the batch but {idx.shape[0]} dataset indices")
+        n_stats, o_loss, o_dbare, o_inst, total = _l._arena_layout(B, C)
+        arena = torch.empty(total, dtype=torch.float32, device=dev)
+        base = arena.data_ptr()
+        ws = _l._workspace(dev, B, C)
+        w, lib, stream = self.embedding.weight, self._lib, _b.stream_ptr(dev)
+        beta1, beta2 = self.group["betas"]
+        with torch.cuda.device(dev):
+            rc = lib.ds_dp_loss_fwd_bwd_indexed(
+                z.data_ptr(), _b.logit_dtype(z), t.data_ptr(), _b.label_dtype(t), _b.ptr(dice_target), B, C, V, w.data_ptr(),
+                _b.ptr(self.fixed), idx.data_ptr(), _b.ptr(self.cw), self.use_risk, _b.ptr(self.scale), None, base,
+                base + 4 * o_loss, base + 4 * o_dbare, base + 4 * o_inst, ws.data_ptr(), ws.numel() * 8, stream)
+            if rc:
+                _b.check(rc, "ds_dp_loss_fwd_bwd_indexed")
+            rc = lib.ds_sparse_adam_scaler_step(
+                w.data_ptr(), self.state["exp_avg"].data_ptr(), self.state["exp_avg_sq"].data_ptr(), idx.data_ptr(),
+                base + 4 * o_dbare, B, w.shape[0], _b.ptr(self.scale), _b.ptr(self.tracker), self.step_count.data_ptr(),
+                self.found_inf.data_ptr(), float(self.group["lr"]), float(beta1), float(beta2), float(self.group["eps"]),
+                self.growth[0], self.growth[1], self.growth[2], stream)
+            if rc:
+                _b.check(rc, "ds_sparse_adam_scaler_step")
+        loss = arena[o_loss]
+        return _l.DPLossOutput(loss, arena, B, C) if return_all else loss

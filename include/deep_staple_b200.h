@@ -174,6 +174,17 @@ int ds_dp_loss_fwd_bwd(const void* logits, int logit_dtype, const void* target, 
                        double* inst_stats, float* loss_out, float* d_bare_weight, float* per_inst_out,
                        void* workspace, size_t workspace_bytes, ds_stream_t stream);
 
+/* The same launch with the data-parameter draw inside the kernel: dp_table = embedding.weight [M] (:418, :741),
+ * fixed_table = fixed_weighting [M] or NULL (:653, :748), idx = b_idxs_dataset [B] (device, in range -- like
+ * torch's embedding the kernel does not check).  Outputs are in batch order (d_bare_weight[b] belongs to row
+ * idx[b]).  With ds_sparse_adam_scaler_step the out-of-line data-parameter step is two launches and no torch op. */
+int ds_dp_loss_fwd_bwd_indexed(const void* logits, int logit_dtype, const void* target, int target_dtype,
+                               const void* dice_target, int64_t B, int64_t C, int64_t V, const float* dp_table,
+                               const float* fixed_table, const int64_t* idx, const float* class_w, int use_risk,
+                               const float* grad_scale, void* dlogits, double* inst_stats, float* loss_out,
+                               float* d_bare_weight, float* per_inst_out, void* workspace, size_t workspace_bytes,
+                               ds_stream_t stream);
+
 /* Data-parallel form with the statistics exchange FUSED into the kernel tail (no NCCL call, no
  * second launch): every rank owns an exchange buffer of ds_dp_loss_exchange_bytes(B_total, C, world)
  * bytes (zero-filled once, 16-byte aligned) that is mapped into all peers (NVLink / NVSwitch peer memory,
@@ -239,6 +250,15 @@ int ds_dp_loss_backward_logits(const void* logits, int logit_dtype, const void* 
 int ds_rescale_inplace(void* x, int dtype, int64_t n, const float* numer, const float* denom,
                        ds_stream_t stream);
 
+/* Backward of scaler_dp.scale(dp_loss).backward() (main_deep_staple.py:762) for the fused loss, ONE launch:
+ *   d_bare_out[b] = d_bare_in[b] * (grad_out / assumed)      the gradient autograd hands to embedding(idx)
+ *   dlogits[i]   *= grad_out / assumed                        only when the two device scalars differ (in place)
+ * d_bare_in / dlogits are what ds_dp_loss_fwd_bwd wrote with grad_scale = `assumed` (NULL: 1); grad_out is the
+ * gradient that actually arrived (the GradScaler's scale in the reference's flow, so nothing is rescaled).
+ * dlogits may be NULL (out-of-line mode). */
+int ds_dp_loss_backward_reconcile(void* dlogits, int dtype, int64_t n, const float* d_bare_in, float* d_bare_out,
+                                  int64_t B, const float* grad_out, const float* assumed, ds_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused data-parameter optimiser step
  *   replaces  scaler_dp.step(optimizer_dp)                       main_deep_staple.py:764-773
@@ -253,6 +273,19 @@ int ds_rescale_inplace(void* x, int dtype, int64_t n, const float* numer, const 
 int ds_sparse_adam_step(float* weight, float* exp_avg, float* exp_avg_sq, const int64_t* idx, const float* grad,
                         int64_t B, int64_t M, const float* scale, float* found_inf, double beta1, double beta2,
                         double eps, double step_size, ds_stream_t stream);
+
+/* scaler_dp.step(optimizer_dp); scaler_dp.update()  (main_deep_staple.py:767-768) in ONE launch with no host-side
+ * state: as ds_sparse_adam_step, plus
+ *   step_count     device int64, SparseAdam's state['step']: advanced only when the step is applied; the bias-corrected
+ *                  step size lr * sqrt(1 - b2^t) / (1 - b1^t) is formed from it on the device in double
+ *   scale, growth_tracker   the GradScaler's own device tensors (_scale fp32, _growth_tracker int32), updated like
+ *                  torch's _amp_update_scale_: scale *= backoff_factor on inf / nan, *= growth_factor after
+ *                  growth_interval consecutive clean steps; both NULL = no scaler (gradients unscaled)
+ *   found_inf      optional float out: 1 if the step was skipped */
+int ds_sparse_adam_scaler_step(float* weight, float* exp_avg, float* exp_avg_sq, const int64_t* idx, const float* grad,
+                               int64_t B, int64_t M, float* scale, int* growth_tracker, long long* step_count,
+                               float* found_inf, double lr, double beta1, double beta2, double eps, double growth_factor,
+                               double backoff_factor, int growth_interval, ds_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Label statistics (per-fold pre-pass and hard Dice)

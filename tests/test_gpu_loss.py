@@ -377,3 +377,67 @@ def test_cuda_graph_capture_and_replay(cuda_device):
         (ref.dp_loss * 256.0).backward()
         assert torch.equal(loss_out[0], ref.dp_loss.detach()) and torch.equal(stats, ref.inst_stats)
         assert torch.equal(dl, zz.grad)
+
+
+def test_public_api_fast_paths_are_bit_identical(cuda_device):
+    """The lean Python layer (one output arena, no autograd node when nothing requires grad, one reconciling launch in
+    backward) must return exactly what the raw C-ABI call returns, in every mode."""
+    import deep_staple_b200 as ds
+    from deep_staple_b200 import _binding as b
+
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(11)
+    B, C, S, M = 5, 2, (8, 16, 16), 20
+    V = S[0] * S[1] * S[2]
+    logits = (2 * torch.randn((B, C, *S), generator=gen)).to(dev)
+    target = (torch.rand((B, *S), generator=gen) < 0.2).long().to(dev)
+    bare = torch.randn(B, generator=gen).to(dev)
+    fixed = (torch.rand(B, generator=gen) * 3 + 1).to(dev)
+    cw = torch.tensor([0.6, 1.4], device=dev)
+    scale = torch.tensor(512.0, device=dev)
+    lib = b.load()
+    dz = torch.empty_like(logits)
+    stats = torch.empty((B, C, 4), dtype=torch.float64, device=dev)
+    loss_out, d_bare, per_inst = torch.empty(2, device=dev), torch.empty(B, device=dev), torch.empty((B, 4), device=dev)
+    ws = torch.zeros((int(lib.ds_dp_loss_workspace_bytes(B, C)) + 7) // 8, dtype=torch.int64, device=dev)
+    rc = lib.ds_dp_loss_fwd_bwd(logits.data_ptr(), b.DS_F32, target.data_ptr(), b.DS_I64, None, B, C, V, bare.data_ptr(),
+                                fixed.data_ptr(), B, 0, cw.data_ptr(), 1, scale.data_ptr(), dz.data_ptr(), stats.data_ptr(),
+                                loss_out.data_ptr(), d_bare.data_ptr(), per_inst.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    # no autograd at all
+    out = ds.dp_weighted_loss(logits, target, bare, fixed, True, grad_scaler=scale, class_weights=cw, return_all=True)
+    assert out.dp_loss.grad_fn is None
+    assert torch.equal(out.dp_loss, loss_out[0]) and torch.equal(out.ce_loss, loss_out[1])
+    assert torch.equal(out.inst_stats, stats) and torch.equal(out.d_bare_weight, d_bare)
+    assert torch.equal(out.per_instance_ce, per_inst[:, 0]) and torch.equal(out.fg_pred, per_inst[:, 1])
+    assert torch.equal(out.instance_weight, per_inst[:, 2])
+    # autograd, GradScaler flow: gradients are the fused pass's, bit for bit
+    z = logits.clone().requires_grad_(True)
+    p = bare.clone().requires_grad_(True)
+    loss = ds.dp_weighted_loss(z, target, p, fixed, True, grad_scaler=scale, class_weights=cw)
+    (loss * scale).backward(retain_graph=True)
+    assert torch.equal(loss.detach(), loss_out[0]) and torch.equal(z.grad, dz) and torch.equal(p.grad, d_bare)
+    # a second backward with ANOTHER incoming gradient (retain_graph): reconciled once, not twice
+    z.grad, p.grad = None, None
+    (loss * (scale * 0.25)).backward()
+    _close(z.grad, dz * 0.25, 1e-6, "second backward, rescaled dlogits")
+    _close(p.grad, d_bare * 0.25, 1e-6, "second backward, rescaled d_bare")
+    # half precision WITHOUT the scale hint: gradients are recomputed in backward, not stored as fp16 subnormals
+    zh = logits.half().requires_grad_(True)
+    ph = bare.clone().requires_grad_(True)
+    lh = ds.dp_weighted_loss(zh, target, ph, fixed, True)
+    (lh * 65536.0).backward()
+    zr = logits.half().requires_grad_(True)
+    lr_ = ds.dp_weighted_loss(zr, target, bare.clone().requires_grad_(True), fixed, True, grad_scaler=65536.0)
+    (lr_ * 65536.0).backward()
+    assert torch.equal(zh.grad, zr.grad), "two-pass backward must equal the fused, pre-scaled gradient"
+    # class-weighted CE: same contract
+    zc = logits.half().requires_grad_(True)
+    ce = ds.weighted_ce(zc, target, cw)
+    (ce * 65536.0).backward()
+    zc2 = logits.half().requires_grad_(True)
+    ce2 = ds.weighted_ce(zc2, target, cw, grad_scaler=65536.0)
+    (ce2 * 65536.0).backward()
+    assert torch.equal(ce.detach(), ce2.detach()) and torch.equal(zc.grad, zc2.grad)
