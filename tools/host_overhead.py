@@ -73,7 +73,7 @@ for name, fn in cases.items():
     print(f"{name:70s} {1e6 * (t1 - t0) / n:7.1f} us host per call", flush=True)
 
 if "--profile" in sys.argv:
-    for name in ("dp_weighted_loss in-line + backward",):
+    for name in ("weighted_ce + backward", "dp_weighted_loss out-of-line + backward"):
         pr = cProfile.Profile()
         pr.enable()
         for _ in range(2000):

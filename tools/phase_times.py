@@ -67,7 +67,7 @@ for rep in range(5):
     line = f"grid {n} event {e0.elapsed_time(e1) * 1000:.1f}us | "
     for k, nm in enumerate(names):
         line += f"{nm} {np.min(rel[:, k]):.1f}/{np.median(rel[:, k]):.1f}/{np.max(rel[:, k]):.1f} "
-    line += f"| last CTA {last}: ticket {rel[last, 6]:.1f} end {rel[last, 7]:.1f} | fill {np.median(rel[:, 9]):.2f} pro {np.median(rel[:, 1]):.2f} | last: fence {rel[last, 5]:.2f} pre {rel[last, 10]:.2f} ticket {rel[last, 6]:.2f} fence2 {rel[last, 11]:.2f} stats {rel[last, 12]:.2f} end {rel[last, 7]:.2f}"
+    line += f"| last CTA {last}: ticket {rel[last, 6]:.1f} end {rel[last, 7]:.1f} | fill {np.median(rel[:, 9]):.2f} pro {np.median(rel[:, 1]):.2f} | last: loop {rel[last, 3]:.2f} flush {rel[last, 4]:.2f} fence/records {rel[last, 5]:.2f} pre {rel[last, 10]:.2f} ticket {rel[last, 6]:.2f} fence2/polled {rel[last, 11]:.2f} stats {rel[last, 12]:.2f} end {rel[last, 7]:.2f} | slowest CTA records/fence {np.max(rel[:, 5]):.2f}"
     print(line)
     if rep == 4 and os.environ.get("DS_DUMP"):
         np.save(os.environ["DS_DUMP"], t)
