@@ -361,7 +361,13 @@ class LossStep:
         gen = torch.Generator(device=device).manual_seed(4242)
         self.bare = torch.randn(self.B_total, generator=gen, device=device)
         self.fixed = (torch.randint(0, 50000, (self.B_total,), generator=gen, device=device).float() + math.e).log() + math.e
+        # class weights are ONE fold-level constant in the reference (main_deep_staple.py:646-651), identical on every
+        # rank: rank 0's (each rank's own label draw would give every rank slightly different weights)
         self.cw = s0["cw"].contiguous()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.broadcast(self.cw, src=0)
         self.scale = torch.tensor(c["grad_scale"], device=device)
         self.stats = torch.zeros((self.B_total, self.C, 4), dtype=torch.float64, device=device)
         self.loss_out = torch.zeros(2, device=device)

@@ -264,7 +264,7 @@ __device__ __forceinline__ float checked_nll(float x, unsigned int* flag, float 
 // global memory (the registers are long gone) and return, in `delta`, how the predicted-class ([0, CC)) and
 // true-positive ([CC, 2 CC)) counts move for voxels where torch.argmax disagrees.  (2) Flag the loss sums the
 // fixed point cannot take and zero them in `nll`.  Both arrays live in the caller's local memory.
-template <typename LT, typename TT, int CC, int VEC>
+template <typename LT, typename TT, int CC, int VEC, bool EQ_RULE>
 __device__ __noinline__ void flagged_step(const LT* __restrict__ zb, const TT* __restrict__ tdb, int64_t V, int64_t off,
                                           int nc, unsigned int* flags, float limit, float* __restrict__ nll,
                                           int* __restrict__ delta) {
@@ -273,8 +273,15 @@ __device__ __noinline__ void flagged_step(const LT* __restrict__ zb, const TT* _
     int am = 0, at = 0;
     for (int c = 1; c < nc; ++c) {
       const float v = Logit<LT>::to_f32(zb[(int64_t)c * V + off + i]);
-      if (v > m) m = v, am = c;                            // the streaming math (strict >, NaN never wins)
+      if (v > m) m = v, am = c;                            // the run-time-C streaming math (strict >, NaN never wins)
       if (mt == mt && (v != v || v > mt)) mt = v, at = c;  // torch.argmax: NaN is the maximum, first one wins
+    }
+    if (EQ_RULE) {  // the compile-time-C streaming math: max ignoring NaN, first logit equal to it, else the last class
+      float mx = Logit<LT>::to_f32(zb[off + i]);
+      for (int c = 1; c < nc; ++c) mx = fmaxf(mx, Logit<LT>::to_f32(zb[(int64_t)c * V + off + i]));
+      am = nc - 1;
+      for (int c = nc - 2; c >= 0; --c)
+        if (Logit<LT>::to_f32(zb[(int64_t)c * V + off + i]) == mx) am = c;
     }
     if (am != at) {
       const int td = (int)tdb[off + i];
@@ -293,9 +300,20 @@ __device__ __forceinline__ void handle_flagged_step(const LT* zb, const TT* tdb,
   int delta[2 * CC];
 #pragma unroll
   for (int c = 0; c < CC; ++c) nll[c] = nll_c[c], delta[c] = 0, delta[CC + c] = 0;
-  flagged_step<LT, TT, CC, VEC>(zb, tdb, V, off, nc, flags, limit, nll, delta);
+  flagged_step<LT, TT, CC, VEC, (CC == 3 || CC == 4)>(zb, tdb, V, off, nc, flags, limit, nll, delta);
 #pragma unroll
   for (int c = 0; c < CC; ++c) nll_c[c] = nll[c], pred_c[c] += delta[c], tp_c[c] += delta[CC + c];
+}
+
+// log(1 + r) for the streaming loop, r in [0, C - 1] (or NaN, which it keeps): a fifth-order series below 1/16
+// (truncation < 2e-7 relative -- confident voxels keep their tiny loss) and the hardware log2 above (MUFU.LG2:
+// absolute error <= 2^-22 on [1, 2], 2 ulp beyond -> <= 1.7e-7 absolute on a term >= 0.06).  9 instructions instead
+// of the 21 of log1p_pos; the loss bound of 1e-5 relative is unaffected (tests/test_gpu_loss.py).
+__device__ __forceinline__ float log1p_fast(float r) {
+  float lg;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(1.0f + r));
+  const float series = r * fmaf(r, fmaf(r, fmaf(r, fmaf(r, 0.2f, -0.25f), 0.33333334f), -0.5f), 1.0f);
+  return r < 0.0625f ? series : lg * 0.69314718056f;
 }
 
 // The epilogue reads the reduced statistics from shared memory when the finishing CTA staged them there
@@ -943,6 +961,20 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     hist = 0u, hist_steps = 0;
   };
 
+  // C == 3 / 4: byte-packed histograms of label, arg-max and true-positive classes (ds_loss_math.inc, HISTC)
+  constexpr bool HISTC = STATS && (C == 3 || C == 4);
+  constexpr bool kFastLog = true;  // log1p_fast (MUFU.LG2) in the C > 2 math; see the TMA shell for the exception
+  unsigned hist_lab = 0u, hist_pred = 0u, hist_tp = 0u;
+  auto empty_histc = [&]() {
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      lab_c[c] += (int)((hist_lab >> (8 * (c & 3))) & 0xffu);
+      pred_c[c] += (int)((hist_pred >> (8 * (c & 3))) & 0xffu);
+      tp_c[c] += (int)((hist_tp >> (8 * (c & 3))) & 0xffu);
+    }
+    hist_lab = hist_pred = hist_tp = 0u, hist_steps = 0;
+  };
+
   // fast binary path (all labels of a warp step in {0,1}): three plain counters instead of the histogram
   int n_t1 = 0, n_am1 = 0, n_both = 0, seen_fast = 0;
   auto merge_fast = [&]() {
@@ -1020,7 +1052,11 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
             if (c > 0) others += pred_step[c], pred_c[c] += pred_step[c];
           }
         }
-        pred_c[0] += VEC - others;  // class 0 = voxels seen - the others
+        if constexpr (HISTC) {
+          if (++hist_steps == kHistSteps) empty_histc();
+        } else {
+          pred_c[0] += VEC - others;  // class 0 = voxels seen - the others
+        }
         if constexpr (PACKED) {
           if (++hist_steps == kHistSteps) empty_hist();
         }
@@ -1039,6 +1075,7 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
   };
   auto flush = [&](int b) {
     if constexpr (PACKED) empty_hist();
+    if constexpr (HISTC) empty_histc();
     merge_fast();
     flush_instance<CC>(p, b, nll_fix, lab_c, pred_c, tp_c);
   };
@@ -1123,6 +1160,7 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
   }
   if (STATS) {
     if constexpr (PACKED) empty_hist();
+    if constexpr (HISTC) empty_histc();
     merge_fast();
     const bool by_warp0 = flush_final<CC>(p, cur_b, nll_fix, lab_c, pred_c, tp_c, uniform_inst && p.claims != nullptr);
     DS_STAMP(4);

@@ -213,6 +213,22 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
     hist = 0u, hist_steps = 0;
   };
 
+  // C == 3 / 4: byte-packed histograms of label, arg-max and true-positive classes (ds_loss_math.inc, HISTC)
+  constexpr bool HISTC = C == 3 || C == 4;
+  // fp32 logits with gradients: this shell sits at its register limit and is scheduled better around the polynomial
+  // log1p (measured, profiles/r02_notes/c3_math_matrix.log: cfg5 211.5 vs 224.2 us, 4 classes 122.7 vs 129.2 us)
+  constexpr bool kFastLog = !(GRAD && sizeof(LT) == 4);
+  unsigned hist_lab = 0u, hist_pred = 0u, hist_tp = 0u;
+  auto empty_histc = [&]() {
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      lab_c[c] += (int)((hist_lab >> (8 * (c & 3))) & 0xffu);
+      pred_c[c] += (int)((hist_pred >> (8 * (c & 3))) & 0xffu);
+      tp_c[c] += (int)((hist_tp >> (8 * (c & 3))) & 0xffu);
+    }
+    hist_lab = hist_pred = hist_tp = 0u, hist_steps = 0;
+  };
+
   for (int64_t k = 0;; ++k) {
     if (threadIdx.x == 0 && !prod_done) produce(k + kTmaStages - 1);
     const int s = (int)(k % kTmaStages);
@@ -283,7 +299,11 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
           nll_fix[c] += __float2ll_rn(nll_c[c] * nll_scale);
           if (c > 0) others += pred_step[c], pred_c[c] += pred_step[c];
         }
-        pred_c[0] += VEC - others;
+        if constexpr (HISTC) {
+          if (++hist_steps == kHistSteps) empty_histc();
+        } else {
+          pred_c[0] += VEC - others;
+        }
         if constexpr (PACKED) {
           if (++hist_steps == kHistSteps) empty_hist();
         }
@@ -299,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
     }
   }
   if constexpr (PACKED) empty_hist();
+  if constexpr (HISTC) empty_histc();
   lab_c[1] += n_t1, lab_c[0] += seen_fast - n_t1;
   tp_c[1] += n_both, tp_c[0] += seen_fast - n_t1 - n_am1 + n_both;
   pred_c[1] += n_am1, pred_c[0] += seen_fast - n_am1;

@@ -44,7 +44,9 @@ def build_snapshot(
     pick = lambda seq, default: tuple((seq[i] if seq is not None else default) for i in order)
     idxs = [torch.as_tensor(dataset_idxs[i]).reshape(()).long() for i in order]
     snap = {
-        "data_parameters": torch.stack([dp[i] for i in order]),
+        # the reference stacks rows of embedding(all_idxs) (:974-977, :1010): a non-leaf that still requires grad, and
+        # torch.save / torch.load keep that flag (probed in SURVEY.md section 8 a10)
+        "data_parameters": torch.stack([dp[i] for i in order]).requires_grad_(True),
         "disturb_flags": tuple(bool(x) for x in pick(disturb_flags, False)),
         "d_ids": pick(d_ids, ""),
         "dataset_idxs": torch.stack(idxs).cpu(),

@@ -58,6 +58,14 @@ def near_tie_mask(lbl_list, weighting_list, rel: float = NEAR_TIE_REL) -> torch.
     return (s - other).abs() < rel * top
 
 
+def multiclass_votes(lbl_list, weighting_list, num_classes: int, dtype=torch.float32) -> torch.Tensor:
+    """``[num_classes, *S]`` weighted votes per class (softmax weights as in consensus.ipynb:103-104)."""
+    stack = torch.stack(list(lbl_list))
+    dense = stack.to_dense() if stack.is_sparse else stack
+    w = softmax_weights(weighting_list).to(dtype)
+    return torch.stack([((dense == c).to(dtype) * w.view(-1, *([1] * (dense.dim() - 1)))).sum(0) for c in range(num_classes)])
+
+
 def calc_multiclass_consensus(lbl_list, weighting_list, num_classes: int) -> torch.Tensor:
     """EXTENSION (no reference counterpart -> parity unpinned): per-class weighted vote with
     argmax, ties -> lowest class index (torch.argmax rule).  For labels in {0,1} and

@@ -118,6 +118,7 @@ def test_snapshot_format_round_trip(tmp_path):
     back = ds.load_snapshot(path)
     assert list(back["d_ids"]) == ["126l:m103r", "127r:m102l", "126l:m102l"]  # sorted ascending by data parameter
     assert back["data_parameters"].shape == (3, 1) and back["data_parameters"].dtype == torch.float32
+    assert back["data_parameters"].requires_grad, "requires_grad must survive save/load like in the reference (SURVEY a10)"
     assert torch.all(back["data_parameters"][1:] >= back["data_parameters"][:-1])
     assert back["dataset_idxs"].tolist() == [9, 2, 5] and back["dataset_idxs"].dtype == torch.int64
     assert back["disturb_flags"] == (True, False, False)

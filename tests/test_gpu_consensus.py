@@ -49,17 +49,26 @@ def test_golden_consensus(cuda_device, name, form):
     assert abs(n_ties - oracle_ties) <= max(2, oracle_ties // 50), (n_ties, oracle_ties)
 
 
-def test_uniform_weights_exact_half_votes_are_bit_exact(cuda_device):
+def test_uniform_weights_mismatches_only_on_near_tie_voxels(cuda_device):
     """Uniform data parameters (the reference's initial state) with an even N give exact-half votes
-    on many voxels.  The kernel forms the same softmax weights (exp(0)=1, 1/N) and adds in ATen's
-    order, so even those knife-edge voxels agree except in ATen's scalar tail columns."""
+    on many voxels (24.5 % of this fixture).  The kernel forms the same softmax weights (exp(0)=1, 1/N) and adds
+    in ATen's order, so most of those knife-edge voxels agree too -- but the contract is only this: every voxel
+    that differs from the reference map lies in the near-tie set (top-two votes within 1e-6 relative,
+    BASELINE.json tolerance clause), and that set's size is reported."""
     import deep_staple_b200 as ds
 
     g = load_golden("consensus__uniform_dp_n10_ties")
     ref = torch.from_numpy(g["consensus"].astype(np.int64))
-    lbls = [torch.from_numpy(l.astype(np.int64)).to(cuda_device) for l in g["labels"]]
-    out = ds.calc_dp_consensus(lbls, [0.0] * 10).cpu()
-    assert (out != ref).float().mean() < 0.02
+    cpu_lbls = [torch.from_numpy(l.astype(np.int64)) for l in g["labels"]]
+    out, n_ties = ds.calc_dp_consensus([l.to(cuda_device) for l in cpu_lbls], [0.0] * 10, return_near_ties=True)
+    out = out.cpu()
+    near = oc.near_tie_mask(cpu_lbls, [0.0] * 10)
+    diff = out != ref
+    assert not bool((diff & ~near).any()), "a voxel outside the near-tie set differs from the reference"
+    print(f"uniform weights: {int(diff.sum())} of {int(near.sum())} near-tie voxels differ ({out.numel()} voxels; "
+          f"kernel counted {int(n_ties)} near ties)")
+    assert int(near.sum()) > 0.2 * out.numel()  # the fixture really is tie-heavy
+    assert abs(int(n_ties) - int(near.sum())) <= max(2, int(near.sum()) // 50)
 
 
 @pytest.mark.parametrize("n", [1, 2, 10, 15, 16, 17, 30, 32, 33, 64, 257, 600])
@@ -174,8 +183,15 @@ def test_multiclass_extension_vs_oracle(cuda_device, k):
     for dt in (torch.int64, torch.uint8):
         out = ds.consensus_multiclass(labels.to(dt).to(cuda_device), dps.to(cuda_device), k)
         for t in range(2):
-            ref = oc.calc_multiclass_consensus(list(labels[t]), [float(x) for x in dps[t]], k)
-            assert (out[t].long().cpu() != ref).float().mean() < 1e-3  # only exact vote ties may differ
+            lb, w = list(labels[t]), [float(x) for x in dps[t]]
+            ref = oc.calc_multiclass_consensus(lb, w, k)
+            # differences only where the two largest class votes are within 1e-6 relative (fp64 votes): the same
+            # exclusion clause as the binary vote -- everywhere else the maps must be identical
+            votes = oc.multiclass_votes(lb, w, k, torch.float64)
+            top2 = votes.topk(2, dim=0).values
+            near = (top2[0] - top2[1]).abs() < 1e-6 * top2[0]
+            diff = out[t].long().cpu() != ref
+            assert not bool((diff & ~near).any()), f"k={k}: a voxel outside the near-tie set differs"
 
 
 def test_snapshot_driver_matches_oracle(cuda_device, tmp_path):
