@@ -7,11 +7,13 @@ reference's own Python call sites.  Hand-written CUDA kernels in a C-ABI shared 
 from ._binding import DeepStapleError, launch_count, lib_path, load  # noqa: F401
 from .consensus import (  # noqa: F401
     calc_dp_consensus,
+    calc_staple_consensus,
     consensus_batched,
     consensus_from_snapshot,
     consensus_multiclass,
     consensus_sparse,
     group_snapshot,
+    staple_batched,
 )
 from .loss import (  # noqa: F401
     DPLossOutput,

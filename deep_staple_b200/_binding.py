@@ -20,7 +20,7 @@ _LIB_PATH = os.environ.get("DS_LIB_PATH") or os.path.join(
 DS_F32, DS_F16, DS_BF16, DS_I64, DS_U8 = 0, 1, 2, 3, 4
 DS_STATS, DS_STAT_NLL, DS_STAT_LABEL, DS_STAT_PRED, DS_STAT_TP = 4, 0, 1, 2, 3
 DS_INST, DS_INST_CE, DS_INST_FG, DS_INST_WEIGHT, DS_INST_SIGMOID = 4, 0, 1, 2, 3
-DS_MAX_CLASSES, DS_MAX_CANDIDATES, DS_MAX_BATCH = 8, 65535, 4096
+DS_MAX_CLASSES, DS_MAX_CANDIDATES, DS_MAX_BATCH, DS_STAPLE_MAX_RATERS = 8, 65535, 4096, 64
 
 _LOGIT_DTYPES = {torch.float32: DS_F32, torch.float16: DS_F16, torch.bfloat16: DS_BF16}
 _LABEL_DTYPES = {torch.int64: DS_I64, torch.uint8: DS_U8}
@@ -37,6 +37,9 @@ SIGNATURES = {
                                              c_void_p, c_int, c_void_p]),
     "ds_consensus_vote_sparse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64,
                                          c_void_p, c_int, c_void_p, c_void_p]),
+    "ds_staple_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "ds_staple": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ds_dp_loss_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "ds_dp_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                    c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

@@ -22,6 +22,8 @@ __all__ = [
     "consensus_batched",
     "consensus_sparse",
     "consensus_multiclass",
+    "calc_staple_consensus",
+    "staple_batched",
     "consensus_from_snapshot",
     "group_snapshot",
 ]
@@ -181,6 +183,58 @@ def calc_dp_consensus(lbl_list: Sequence[torch.Tensor], weighting_list, *, devic
     return res.to(src_device)
 
 
+def staple_batched(labels: torch.Tensor, *, max_iterations: int = 200, foreground: int = 1, return_probability: bool = False):
+    """Binary STAPLE (EM) for ``T`` targets at once (``ds_staple``): ``labels [T, N, *spatial]`` int64 / uint8 on the
+    GPU, ``N <= 64`` raters.  Returns ``(consensus [T, *spatial], sensitivity [T, N] float64, specificity [T, N] float64,
+    iterations [T] int32)`` (+ the probability map ``[T, *spatial]`` fp32 with ``return_probability``), all on the
+    device.  The comparison baseline of the consensus notebook (consensus.ipynb:112-124: SimpleITK's
+    ``STAPLEImageFilter`` with foreground 1.0 and at most 200 iterations) -- PARITY UNPINNED, see oracle/staple.py."""
+    _b.require_cuda(labels, "labels")
+    if labels.dim() < 3:
+        raise ValueError(f"labels must be [T, N, *spatial], got {tuple(labels.shape)}")
+    T, N = labels.shape[0], labels.shape[1]
+    spatial = tuple(labels.shape[2:])
+    V = labels[0, 0].numel()
+    stride = (V + 3) // 4 * 4  # the kernel reads whole words: planes padded to a multiple of 4 voxels (padding votes nothing)
+    lab = labels.reshape(T, N, V)
+    lab = torch.nn.functional.pad(lab, (0, stride - V)) if stride != V else lab.contiguous()
+    dev = lab.device
+    out = torch.empty((T, stride), dtype=lab.dtype, device=dev)
+    prob = torch.empty((T, stride), dtype=torch.float32, device=dev) if return_probability else None
+    sens = torch.zeros((T, N), dtype=torch.float64, device=dev)
+    spec = torch.zeros((T, N), dtype=torch.float64, device=dev)
+    iters = torch.zeros(T, dtype=torch.int32, device=dev)
+    lib = _b.load()
+    ws = torch.empty((int(lib.ds_staple_workspace_bytes(T, N)) + 7) // 8, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.ds_staple(_b.ptr(lab), _b.label_dtype(lab), T, N, V, stride, int(foreground), int(max_iterations), _b.ptr(out),
+                           _b.label_dtype(out), _b.ptr(prob), _b.ptr(sens), _b.ptr(spec), _b.ptr(iters), _b.ptr(ws),
+                           ws.numel() * 8, _b.stream_ptr(dev))
+    _b.check(rc, "ds_staple")
+    res = (out[:, :V].reshape(T, *spatial), sens, spec, iters)
+    return res + (prob[:, :V].reshape(T, *spatial),) if return_probability else res
+
+
+def calc_staple_consensus(lbl_list: Sequence[torch.Tensor], *, max_iterations: int = 200, device=None):
+    """Drop-in for the notebook's ``calc_staple_consensus(lbl_list)`` (consensus.ipynb:112-124): returns
+    ``(consensus int64 [D,H,W] on the labels' device, sensitivities, specificities)`` -- the two lists of python
+    floats that ``GetSensitivity()`` / ``GetSpecificity()`` return there.  ``lbl_list``: N sparse-COO or dense label
+    volumes; foreground is label value 1 (``SetForegroundValue(1.0)``), at most ``max_iterations`` EM iterations
+    (``SetMaximumIterations(200)``)."""
+    lbls = list(lbl_list)
+    if not lbls:
+        raise ValueError("lbl_list is empty")
+    src_device = lbls[0].device
+    dev = _cuda_device(device if device is not None else (src_device if src_device.type == "cuda" else None))
+    dense = [(l.to(dev).to_dense() if l.is_sparse else l.to(dev)) for l in lbls]
+    stack = torch.stack([d if d.dtype == torch.uint8 else d.to(torch.int64) for d in dense]).unsqueeze(0)
+    if stack.dtype == torch.int64:  # the notebook casts to int16 anyway (:118); bytes are 8x lighter
+        stack = stack.clamp_(0, 255).to(torch.uint8)
+    out, sens, spec, _ = staple_batched(stack, max_iterations=max_iterations)
+    cons = out[0].long().to(src_device)
+    return cons, [float(x) for x in sens[0].cpu()], [float(x) for x in spec[0].cpu()]
+
+
 def consensus_multiclass(labels: torch.Tensor, data_parameters: torch.Tensor, num_classes: int,
                          *, out_dtype: Optional[torch.dtype] = None, weights_are_softmaxed: bool = False) -> torch.Tensor:
     """EXTENSION without a reference counterpart: per-class weighted vote + argmax (ties -> lowest
@@ -330,8 +384,28 @@ def _batched_snapshot_vote(snapshot, dicts, dev):
     return out, f_ids, shape
 
 
-def consensus_from_snapshot(snapshot, *, device=None, with_dice: bool = True) -> Dict[str, Dict]:
-    """The consensus driver cell (consensus.ipynb:353-418) minus the SimpleITK STAPLE baseline:
+def _add_staple(dicts: Dict[str, Dict], device, with_dice: bool) -> None:
+    """The STAPLE half of the driver cell (consensus.ipynb:393-396, 408-418): per target ``staple_consensus`` (sparse),
+    ``staple_consensus_oracle_dice`` and per moving atlas ``staple_sensitivity``."""
+    from .metrics import dice_from_label_maps
+
+    for f_id, fixed in dicts.items():
+        ids = [k for k, e in fixed.items() if isinstance(e, dict)]
+        cons, sens, _ = calc_staple_consensus([fixed[k]["warped_label"] for k in ids], device=device)
+        for k, s in zip(ids, sens):
+            fixed[k]["staple_sensitivity"] = s
+        fixed["staple_consensus"] = cons.cpu().to_sparse()
+        if with_dice:
+            expert = fixed["expert_label"]
+            expert = expert.to_dense() if expert.is_sparse else expert
+            fixed["staple_consensus_oracle_dice"] = dice_from_label_maps(
+                cons.cpu().unsqueeze(0), expert.cpu().unsqueeze(0), 2, nan_for_unlabeled_target=False)
+
+
+def consensus_from_snapshot(snapshot, *, device=None, with_dice: bool = True, with_staple: bool = False) -> Dict[str, Dict]:
+    """The consensus driver cell (consensus.ipynb:353-418); ``with_staple`` adds the STAPLE baseline's keys
+    (``staple_consensus``, ``staple_consensus_oracle_dice``, ``<m_id>.staple_sensitivity``) from the GPU EM of
+    ``calc_staple_consensus`` instead of SimpleITK's filter (parity unpinned, hence off by default):
     ``snapshot`` is the dict saved as ``train_label_snapshot.pth`` (main_deep_staple.py:963-1037) or
     a path to it.  Per target: vote over all its registered candidates, Dice against the expert label,
     results stored under ``dp_consensus`` (sparse, like the notebook) / ``dp_consensus_oracle_dice``.
@@ -366,6 +440,8 @@ def consensus_from_snapshot(snapshot, *, device=None, with_dice: bool = True) ->
                                                                 check_invariants=False).cpu()
             if dice is not None:
                 dicts[f_id]["dp_consensus_oracle_dice"] = dice[i : i + 1]
+        if with_staple:
+            _add_staple(dicts, device, with_dice)
         return dicts
     for f_id, fixed in dicts.items():
         entries = [e for e in fixed.values() if isinstance(e, dict)]
@@ -382,4 +458,6 @@ def consensus_from_snapshot(snapshot, *, device=None, with_dice: bool = True) ->
                 cons.unsqueeze(0), expert.unsqueeze(0), 2, nan_for_unlabeled_target=False
             )
         dicts[f_id] = fixed
+    if with_staple:
+        _add_staple(dicts, device, with_dice)
     return dicts

@@ -69,10 +69,19 @@ class FusedExchange:
 
     @classmethod
     def get(cls, b_total: int, num_classes: int, device: torch.device, group=None) -> "FusedExchange":
+        """The exchange of (group, global batch, classes), built on first use -- a COLLECTIVE (rendezvous + barrier):
+        call it explicitly on every rank before the first step if that step is going to be captured in a CUDA graph.
+        At most 8 exchanges are kept (a training run uses one or two); ``clear_cache()`` drops them all."""
         key = (id(group), b_total, num_classes, device.index)
         if key not in cls._cache:
+            if len(cls._cache) >= 8:
+                cls._cache.pop(next(iter(cls._cache)))
             cls._cache[key] = cls(b_total, num_classes, device, group)
         return cls._cache[key]
+
+    @classmethod
+    def clear_cache(cls) -> None:
+        cls._cache.clear()
 
     def check(self) -> None:
         """Raise if this rank ever lost a step (a peer's statistics did not arrive within

@@ -14,6 +14,24 @@ from . import _binding as _b
 
 __all__ = ["dp_optimizer_step", "LossSection"]
 
+import os
+
+
+def _check_unique(idx: torch.Tensor) -> None:
+    """``DS_DEBUG=1``: the optimiser kernels assume unique rows per batch (the reference's ``SubsetRandomSampler``,
+    main_deep_staple.py:597, guarantees it; torch's SparseAdam would coalesce duplicates, the kernels would race)."""
+    if os.environ.get("DS_DEBUG") and idx.unique().numel() != idx.numel():
+        raise ValueError("b_idxs_dataset contains duplicate rows: the fused data-parameter step needs unique indices")
+
+
+def _require_scaler_internals(scaler) -> None:
+    """The fused steps read / write private GradScaler state; fail loudly if a torch upgrade moved it."""
+    for attr in ("_scale", "_growth_tracker", "_per_optimizer_states", "_lazy_init_scale_growth_tracker",
+                 "get_growth_factor", "get_backoff_factor", "get_growth_interval"):
+        if not hasattr(scaler, attr):
+            raise RuntimeError(f"torch.amp.GradScaler has no attribute {attr!r} in torch {torch.__version__}: "
+                               "deep_staple_b200's fused optimiser step does not support this torch version")
+
 
 def dp_optimizer_step(
     embedding: torch.nn.Embedding,
@@ -60,8 +78,10 @@ def dp_optimizer_step(
     if idx.numel() != grad.numel():
         raise ValueError(f"{idx.numel()} indices but {grad.numel()} gradients")
     enabled = scaler_dp is not None and scaler_dp.is_enabled()
+    _check_unique(idx)
     scale = None
     if enabled:
+        _require_scaler_internals(scaler_dp)
         scale = scaler_dp._scale
         if scale is None:
             raise RuntimeError("the GradScaler has not scaled a loss yet: pass the same scaler to dp_weighted_loss(grad_scaler=...)")
@@ -141,11 +161,7 @@ class LossSection:
         self.scale = self.tracker = None
         self.growth = (2.0, 0.5, 2000)
         if scaler_dp is not None and scaler_dp.is_enabled():
-            # private GradScaler state: fail loudly if a torch upgrade renames it instead of silently mis-scaling
-            for attr in ("_scale", "_growth_tracker", "_lazy_init_scale_growth_tracker", "get_growth_factor",
-                         "get_backoff_factor", "get_growth_interval"):
-                if not hasattr(scaler_dp, attr):
-                    raise RuntimeError(f"torch.amp.GradScaler has no attribute {attr!r}: unsupported torch version")
+            _require_scaler_internals(scaler_dp)  # private state: fail loudly instead of silently mis-scaling
             if scaler_dp._scale is None:
                 scaler_dp._lazy_init_scale_growth_tracker(dev)
             self.scale, self.tracker = scaler_dp._scale, scaler_dp._growth_tracker
@@ -173,6 +189,7 @@ class LossSection:
             idx = idx.detach().to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
         if idx.shape[0] != B:
             raise ValueError(f"{B} instances in the batch but {idx.shape[0]} dataset indices")
+        _check_unique(idx)
         n_stats, o_loss, o_dbare, o_inst, total = _l._arena_layout(B, C)
         arena = torch.empty(total, dtype=torch.float32, device=dev)
         base = arena.data_ptr()

@@ -58,6 +58,7 @@ typedef enum ds_status {
 #define DS_MAX_CLASSES 8        /* loss / Dice statistics kernels */
 #define DS_MAX_CANDIDATES 65535 /* atlas candidates per target in the vote */
 #define DS_MAX_BATCH 4096       /* instances of one (global) batch in the loss epilogue */
+#define DS_STAPLE_MAX_RATERS 64 /* label candidates per target in the STAPLE baseline */
 
 /* per-class record layout of `inst_stats` ([B_total, C, DS_STATS] doubles) */
 #define DS_STATS 4
@@ -123,6 +124,27 @@ int ds_consensus_vote_sparse(const int64_t* voxel_index, const int64_t* values, 
                              const float* weights, int weights_are_raw, int64_t T, int64_t N, int64_t V,
                              void* out, int out_dtype, unsigned long long* near_tie_count,
                              ds_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Binary STAPLE (expectation-maximisation) baseline
+ *   replaces  calc_staple_consensus, deep_staple/consensus/consensus.ipynb:112-124
+ *             (sitk.STAPLEImageFilter: SetForegroundValue(1.0), SetMaximumIterations(200), Execute,
+ *              GetSensitivity / GetSpecificity) -- third-party ITK, not part of the reference tree: the
+ *             published algorithm (Warfield et al., IEEE TMI 2004) in the form ITK's filter runs it; PARITY
+ *             UNPINNED (oracle/staple.py restates the same equations in fp64).
+ * labels [T, N, plane_stride] as for ds_consensus_vote, V valid voxels at the start of every plane (plane_stride >= V, a
+ * multiple of 4 elements; N <= DS_STAPLE_MAX_RATERS raters per target; 16-byte aligned).  out [T, plane_stride] (labels'
+ * dtype): probability > 0.5.  prob [T, plane_stride] float or NULL: the probability map.
+ * sensitivity / specificity [T, N] doubles or both NULL; iterations [T] ints or NULL: EM iterations run.
+ * Enqueues max_iterations + 1 launches (one streaming pass over the labels each; nothing is stored per voxel between
+ * iterations); targets that converged (no p_j / q_j moved by more than 1e-7) skip the remaining ones.  No host sync.
+ * workspace: ds_staple_workspace_bytes(T, N) bytes, 16-byte aligned (cleared by the call).
+ * ------------------------------------------------------------------------------------------- */
+size_t ds_staple_workspace_bytes(int64_t T, int64_t N);
+int ds_staple(const void* labels, int label_dtype, int64_t T, int64_t N, int64_t V, int64_t plane_stride, int foreground,
+              int max_iterations,
+              void* out, int out_dtype, float* prob, double* sensitivity, double* specificity, int* iterations,
+              void* workspace, size_t workspace_bytes, ds_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Data-parameter-weighted loss, fused forward + backward
