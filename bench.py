@@ -58,8 +58,8 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused loss kernel on this workload,
 # from the `ncu --set full` capture summarised in profiles/ (268.5 MB read + 95.95 MB written; the rest of
 # the 134 MB of gradients is still dirty in L2 at kernel end)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 364_468_736
-NCU_TRAFFIC_SOURCE = "profiles/r01_loss_fwdbwd_ncu_summary.txt"
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 365_473_792
+NCU_TRAFFIC_SOURCE = "profiles/r02_loss_f32_ncu_summary.txt"
 
 LOSS_CFG = dict(B=8, C=2, S=(128, 128, 128), M=600, grad_scale=65536.0)
 VOTE_CFG = dict(T_global=100, N=30, S=(128, 128, 128))
