@@ -871,7 +871,7 @@ def vote_section(device, rank, world, steps, warmup, peak, dist, dtypes=("int64"
             gms = float(gsec.item()) / gsteps * 1e3
             rec["ms_vote_plus_gather"] = gms
             rec["ms_gather"] = gms - rec["ms_vote"]
-            rec["gather_bytes_received_per_rank"] = (-(-c["T_global"] // world)) * world * V * sz
+            rec["gather_bytes_received_per_rank"] = (-(-c["T_global"] // world)) * world * V  # uint8 maps travel, widened on arrival
             rec["gvoxel_candidates_per_s_with_gather"] = c["T_global"] * c["N"] * V / (gms / 1e3) / 1e9
         out[name] = rec
         del labels, res

@@ -97,9 +97,11 @@ int setup_geometry(LossParams& p, int logit_dtype, int target_dtype, bool* vec_o
   if (env_int("DS_FORCE_SCALAR", 0)) vec = false;
   p.units = vec ? p.V / W : p.V;
   *vec_out = vec;
-  // Round 2, after the C > 2 math went mask-based (ds_loss_math.inc; profiles/r02_notes/c3_math_matrix.log, us TMA vs LDG):
-  // fp32 C >= 3 with gradients 211.5 vs 217.6 (C = 3), 122.7 vs 127.2 (C = 4): still TMA; fp32 C = 3 forward only 153.8 vs
-  // 133.5 and half logits C = 3 195.1 vs 182.5: LDG.  The older notes below are round 1's.
+  // Round 2, after the C > 2 math was rewritten for the two arithmetic pipes (ds_loss_math.inc: one-hot products, min / max
+  // network, packed histograms; profiles/r02_notes/c3_math_matrix2.log, us TMA vs LDG): fp32 C = 3 with gradients 223.9 vs
+  // 203.3, forward only 149.8 vs 131.9, half logits C = 3 183.9 vs 157.8, fp32 C = 4 129.9 vs 118.6 -- the LDG shell (3 resident
+  // CTAs per SM at 80 registers) now wins every C > 2 case; the TMA shell keeps half-precision C = 2 with gradients.
+  // The older notes below are round 1's.
   // TMA-staged shell (ds_loss_tma.cuh): vector path, statistics on, no separate Dice target, C in {2,3,4},
   // every bulk copy a multiple of 16 bytes, one group of CTAs per instance.  Which shell wins was measured per
   // variant on B200 after the LDG shell got its dynamic tail (profiles/r01_notes/shell_matrix.log, cfg2 / cfg5
@@ -110,8 +112,7 @@ int setup_geometry(LossParams& p, int logit_dtype, int target_dtype, bool* vec_o
   // voxels x three planes per thread cost the TMA shell its registers).  DS_LOSS_TMA=0/1 overrides.
   const bool eligible = vec && stats && !p.dice_target && C >= 2 && C <= 4 && (p.V % 16 == 0) &&
                         p.B_local <= (int64_t)sm_count() * env_int("DS_LOSS_TMA_CTAS_PER_SM", kTmaMinBlocks);
-  const bool heavy = (C >= 3 && logit_dtype == DS_F32 && p.dlogits != nullptr) ||
-                     (C == 2 && logit_dtype != DS_F32 && target_dtype == DS_I64 && p.dlogits != nullptr);
+  const bool heavy = C == 2 && logit_dtype != DS_F32 && target_dtype == DS_I64 && p.dlogits != nullptr;
   const int choice = env_int("DS_LOSS_TMA", -1);
   p.use_tma = eligible && (choice < 0 ? heavy : choice != 0);
   const int rc = setup_tiles(p, who, stats);

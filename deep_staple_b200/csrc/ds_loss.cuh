@@ -193,6 +193,16 @@ __device__ __forceinline__ float amax3_nan(float a, float b, float c) {
       : "f"(a), "f"(b), "f"(c));
   return d;
 }
+__device__ __forceinline__ float fmin_nan(float a, float b) {
+  float d;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
 template <int CC, int VEC>
 __device__ __forceinline__ bool lane_suspicious(const float (&z)[CC][VEC], int nc) {
   float acc = 0.f;
@@ -264,24 +274,23 @@ __device__ __forceinline__ float checked_nll(float x, unsigned int* flag, float 
 // global memory (the registers are long gone) and return, in `delta`, how the predicted-class ([0, CC)) and
 // true-positive ([CC, 2 CC)) counts move for voxels where torch.argmax disagrees.  (2) Flag the loss sums the
 // fixed point cannot take and zero them in `nll`.  Both arrays live in the caller's local memory.
-template <typename LT, typename TT, int CC, int VEC, bool EQ_RULE>
-__device__ __noinline__ void flagged_step(const LT* __restrict__ zb, const TT* __restrict__ tdb, int64_t V, int64_t off,
-                                          int nc, unsigned int* flags, float limit, float* __restrict__ nll,
+template <typename LT, typename TT, int CC, int VEC, bool RECOMPUTE>
+__device__ __noinline__ void flagged_step(const LT* __restrict__ zb, const TT* __restrict__ tb, const TT* __restrict__ tdb, int64_t V,
+                                          int64_t off, int nc, unsigned int* flags, float limit, float* __restrict__ nll,
                                           int* __restrict__ delta) {
+  const float inf = __int_as_float(0x7f800000);
+  if (RECOMPUTE)
+    for (int c = 0; c < nc; ++c) nll[c] = 0.f;
   for (int i = 0; i < VEC; ++i) {
     float m = Logit<LT>::to_f32(zb[off + i]), mt = m;
     int am = 0, at = 0;
     for (int c = 1; c < nc; ++c) {
       const float v = Logit<LT>::to_f32(zb[(int64_t)c * V + off + i]);
-      if (v > m) m = v, am = c;                            // the run-time-C streaming math (strict >, NaN never wins)
+      // the streaming math's arg-max (strict >, first maximum wins; a NaN never wins): the compile-time-C form
+      // keeps the running maximum with fmaxf (a leading NaN is dropped), the run-time-C form with the compare itself
+      if (v > m) am = c;
+      m = RECOMPUTE ? fmaxf(m, v) : ((v > m) ? v : m);
       if (mt == mt && (v != v || v > mt)) mt = v, at = c;  // torch.argmax: NaN is the maximum, first one wins
-    }
-    if (EQ_RULE) {  // the compile-time-C streaming math: max ignoring NaN, first logit equal to it, else the last class
-      float mx = Logit<LT>::to_f32(zb[off + i]);
-      for (int c = 1; c < nc; ++c) mx = fmaxf(mx, Logit<LT>::to_f32(zb[(int64_t)c * V + off + i]));
-      am = nc - 1;
-      for (int c = nc - 2; c >= 0; --c)
-        if (Logit<LT>::to_f32(zb[(int64_t)c * V + off + i]) == mx) am = c;
     }
     if (am != at) {
       const int td = (int)tdb[off + i];
@@ -289,18 +298,34 @@ __device__ __noinline__ void flagged_step(const LT* __restrict__ zb, const TT* _
       if (td == at) delta[CC + at] += 1;
       if (td == am) delta[CC + am] -= 1;
     }
+    if (RECOMPUTE) {
+      // this voxel's loss term with torch's log-softmax semantics (mt: NaN if any logit is NaN, else the maximum):
+      // x - max - log(sum exp(x - max)) is NaN for every class when max is NaN / +inf or all logits are -inf
+      const int t = (int)tb[off + i];
+      if ((unsigned)t < (unsigned)nc) {
+        float v = mt - mt;  // NaN for a non-finite maximum, else 0
+        if (fabsf(mt) < inf) {
+          float rest = 0.f;
+          for (int c = 0; c < nc; ++c)
+            if (c != at) rest += expf(Logit<LT>::to_f32(zb[(int64_t)c * V + off + i]) - mt);
+          v = log1pf(rest) + (mt - Logit<LT>::to_f32(zb[(int64_t)t * V + off + i]));
+        }
+        nll[t] += v;
+      }
+    }
   }
   for (int c = 0; c < nc; ++c) nll[c] = checked_nll(nll[c], flags + c, limit);
 }
 template <typename LT, typename TT, int CC, int VEC>
-__device__ __forceinline__ void handle_flagged_step(const LT* zb, const TT* tdb, int64_t V, int64_t off, int nc,
+__device__ __forceinline__ void handle_flagged_step(const LT* zb, const TT* tb, const TT* tdb, int64_t V, int64_t off, int nc,
                                                     float (&nll_c)[CC], int (&pred_c)[CC], int (&tp_c)[CC],
                                                     unsigned int* flags, float limit) {
   float nll[CC];      // addressable on purpose: local memory, inside this cold branch only
   int delta[2 * CC];
 #pragma unroll
   for (int c = 0; c < CC; ++c) nll[c] = nll_c[c], delta[c] = 0, delta[CC + c] = 0;
-  flagged_step<LT, TT, CC, VEC, (CC == 3 || CC == 4)>(zb, tdb, V, off, nc, flags, limit, nll, delta);
+  // compile-time C = 3 / 4: the streaming math uses one-hot products, so a flagged step's sums are redone here
+  flagged_step<LT, TT, CC, VEC, (CC == 3 || CC == 4)>(zb, tb, tdb, V, off, nc, flags, limit, nll, delta);
 #pragma unroll
   for (int c = 0; c < CC; ++c) nll_c[c] = nll[c], pred_c[c] += delta[c], tp_c[c] += delta[CC + c];
 }
@@ -1040,7 +1065,7 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
           }
         } else {
           if (sums_suspicious<CC>(nll_c, nc, nll_limit))  // cold: NaN / inf / out-of-range loss sum in this lane's step
-            handle_flagged_step<LT, TT, CC, VEC>(zb, DICE ? db : tb, V, (int64_t)off, nc, nll_c, pred_c, tp_c,
+            handle_flagged_step<LT, TT, CC, VEC>(zb, tb, DICE ? db : tb, V, (int64_t)off, nc, nll_c, pred_c, tp_c,
                                                  p.flags + cur_b * nc, nll_limit);
         }
         // this lane's fp32 loss sums of the step (fixed voxels, fixed order) become exact integers

@@ -215,9 +215,7 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
 
   // C == 3 / 4: byte-packed histograms of label, arg-max and true-positive classes (ds_loss_math.inc, HISTC)
   constexpr bool HISTC = C == 3 || C == 4;
-  // fp32 logits with gradients: this shell sits at its register limit and is scheduled better around the polynomial
-  // log1p (measured, profiles/r02_notes/c3_math_matrix.log: cfg5 211.5 vs 224.2 us, 4 classes 122.7 vs 129.2 us)
-  constexpr bool kFastLog = !(GRAD && sizeof(LT) == 4);
+  constexpr bool kFastLog = true;  // log1p_fast (MUFU.LG2) in the C > 2 math
   unsigned hist_lab = 0u, hist_pred = 0u, hist_tp = 0u;
   auto empty_histc = [&]() {
 #pragma unroll
@@ -291,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
           }
         } else {
           if (sums_suspicious<CC>(nll_c, nc, nll_limit))  // cold: NaN / inf / out-of-range loss sum in this lane's row
-            handle_flagged_step<LT, TT, CC, VEC>(zb, tb, V, v, nc, nll_c, pred_c, tp_c, p.flags + b * nc, nll_limit);
+            handle_flagged_step<LT, TT, CC, VEC>(zb, tb, tb, V, v, nc, nll_c, pred_c, tp_c, p.flags + b * nc, nll_limit);
         }
         int others = 0;
 #pragma unroll
