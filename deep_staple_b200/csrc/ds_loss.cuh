@@ -87,6 +87,10 @@ struct LossParams {
   int rank, world;
 };
 
+// programmatic dependent launch (see launch_kernel in ds_loss_launch.cuh); both are no-ops in a plainly launched grid
+__device__ __forceinline__ void pdl_wait_for_previous_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release_next_grid() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Tuning builds only (-DDS_TIMING, never the shipped library): per-CTA %globaltimer stamps of the kernel
 // phases, read back with ds_debug_read (ds_loss_f32.cu) by tools/phase_times.py.
 #ifdef DS_TIMING
@@ -1144,6 +1148,9 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     // instance (warp w of every CTA of the group shares counter w: ~75 warps from as many SMs, <= 50
     // same-address atomics per us), still in address order, so the front stays narrow.  The claim for the
     // next step is in flight while the current one is processed.
+    // first access to the workspace (claim counters, then the accumulators and tickets of the tail): from here on the
+    // previous grid -- which may still be in its tail if this one was launched programmatically -- must be complete
+    pdl_wait_for_previous_grid();
     if (p.claims) {
       cur_b = b;
       if (wg >= n_steps) coef0 = home.have_home ? home.coef_home : instance_coef(b);
@@ -1161,6 +1168,7 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
     }
     DS_STAMP(3);
   } else {
+    pdl_wait_for_previous_grid();  // this schedule flushes into the workspace whenever a warp changes instance
     const StepWalk walk(p);
     int b = walk.b0;
     int64_t s_in = walk.s_in0;  // step inside instance b
@@ -1183,6 +1191,11 @@ __global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel
       if (u < p.units) process(zb, tb, db, gb, u * VEC);
     }
   }
+  // This CTA has streamed its share: the next grid may move in behind it.  All of this CTA's reads have returned by
+  // now; its gradient stores are fenced first, so that a next launch that was handed the same (freed and reused)
+  // gradient buffer cannot have an early store overtaken by one of ours that is still in flight.
+  if (GRAD) __threadfence();
+  pdl_release_next_grid();
   if (STATS) {
     if constexpr (PACKED) empty_hist();
     if constexpr (HISTC) empty_histc();

@@ -6,6 +6,25 @@
 
 namespace ds {
 
+// Launch with programmatic stream serialisation allowed (programmatic dependent launch): if the kernel right before
+// this one in the stream is one of ours that has executed griddepcontrol.launch_dependents (every CTA, after its
+// streaming loop), this grid's CTAs may become resident while that kernel's tail is still running; they do their
+// prologue and stream their static share, and stop at griddepcontrol.wait -- placed before their first access to the
+// workspace -- until the previous grid has completed and flushed.  After any other kernel (cuDNN, the optimiser
+// step, ...) the attribute changes nothing: a kernel that never triggers releases its dependents only on completion.
+// DS_LOSS_PDL=0 launches the plain way.
+template <typename K>
+void launch_kernel(K kernel, dim3 grid, int smem, cudaStream_t stream, const LossParams& p) {
+  static const bool pdl = env_int("DS_LOSS_PDL", 1) != 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = (size_t)smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, p);  // errors surface through check_launch (cudaPeekAtLastError)
+}
+
 template <typename LT, typename TT, int C, int VEC>
 int launch_cfg(const LossParams& p, bool grad, bool stats, cudaStream_t stream) {
   const dim3 grid((unsigned)p.grid);
@@ -16,7 +35,7 @@ int launch_cfg(const LossParams& p, bool grad, bool stats, cudaStream_t stream) 
       auto launch = [&](auto kernel) -> int {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail((int)e, "loss_kernel_tma: %s", cudaGetErrorString(e));
-        kernel<<<grid, kThreads, smem, stream>>>(p);
+        launch_kernel(kernel, grid, smem, stream, p);
         count_launch();
         return check_launch("loss_kernel_tma");
       };
@@ -24,13 +43,13 @@ int launch_cfg(const LossParams& p, bool grad, bool stats, cudaStream_t stream) 
     }
   }
   if (grad && stats) {
-    if (dice) loss_kernel<LT, TT, C, VEC, true, true, true><<<grid, kThreads, 0, stream>>>(p);
-    else loss_kernel<LT, TT, C, VEC, true, true, false><<<grid, kThreads, 0, stream>>>(p);
+    if (dice) launch_kernel(loss_kernel<LT, TT, C, VEC, true, true, true>, grid, 0, stream, p);
+    else launch_kernel(loss_kernel<LT, TT, C, VEC, true, true, false>, grid, 0, stream, p);
   } else if (stats) {
-    if (dice) loss_kernel<LT, TT, C, VEC, false, true, true><<<grid, kThreads, 0, stream>>>(p);
-    else loss_kernel<LT, TT, C, VEC, false, true, false><<<grid, kThreads, 0, stream>>>(p);
+    if (dice) launch_kernel(loss_kernel<LT, TT, C, VEC, false, true, true>, grid, 0, stream, p);
+    else launch_kernel(loss_kernel<LT, TT, C, VEC, false, true, false>, grid, 0, stream, p);
   } else {
-    loss_kernel<LT, TT, C, VEC, true, false, false><<<grid, kThreads, 0, stream>>>(p);
+    loss_kernel<LT, TT, C, VEC, true, false, false><<<grid, kThreads, 0, stream>>>(p);  // no tail, no workspace
   }
   count_launch();
   return check_launch("loss_kernel");

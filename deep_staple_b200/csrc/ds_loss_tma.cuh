@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
 
   // Launch ramp: the first tiles go out before the prologue (data-parameter loads, sigmoids, divisions),
   // which would otherwise leave DRAM idle for its ~1.5 us.
+  if (dynamic) pdl_wait_for_previous_grid();  // the claim counters live in the workspace
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < kTmaStages; ++s) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], kWarps);
@@ -316,6 +317,9 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
       }
     }
   }
+  if (GRAD) __threadfence();     // gradient stores performed before the next grid may reuse the buffer (see ds_loss.cuh)
+  pdl_release_next_grid();       // this CTA has streamed its tiles: the next grid may move in behind it
+  pdl_wait_for_previous_grid();  // and from here on (accumulators, tickets) the previous one must be complete
   if constexpr (PACKED) empty_hist();
   if constexpr (HISTC) empty_histc();
   lab_c[1] += n_t1, lab_c[0] += seen_fast - n_t1;
