@@ -359,6 +359,13 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
       store_labels<OT, VPT>(out_t + u * VPT, on);
     }
   }
+  // Programmatic dependent launch: this CTA has read all its labels and its map stores are fenced -- a vote (or loss)
+  // kernel launched right behind this one may move in while the last CTAs finish (nothing it reads is written here; a
+  // reused output buffer cannot see one of our stores arrive late).  The wait before exit keeps stream order for
+  // whatever follows the next kernel.  Both are no-ops for a plainly launched grid.
+  __threadfence();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (TIES) {
     my_ties = (unsigned int)warp_sum((int)my_ties);
     if ((threadIdx.x & 31) == 0 && my_ties) atomicAdd(&s_ties, my_ties);
@@ -438,7 +445,16 @@ int launch_vote(const VoteParams& p0, cudaStream_t stream) {
   if (p.T * want > 0x7fffffffLL) return fail(DS_ERR_SHAPE, "ds_consensus_vote: T*chunks exceeds the grid limit");
   p.chunks = (int)want;
   const dim3 grid((unsigned)(p.T * want));
-  kern<<<grid, kThreads, smem, stream>>>(p);
+  {
+    static const bool pdl = env_int("DS_VOTE_PDL", 1) != 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, p);
+  }
   count_launch();
   return check_launch("ds_consensus_vote");
 }
