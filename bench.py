@@ -58,9 +58,9 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused loss kernel on this workload,
 # from the `ncu --set full` capture summarised in profiles/ (268.5 MB read + 95.95 MB written; the rest of
 # the 134 MB of gradients is still dirty in L2 at kernel end)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 365_473_792
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 366_477_824
 NCU_TRAFFIC_SOURCE = "profiles/r02_loss_f32_ncu_summary.txt"
-NCU_ISOLATED_US = 69.12  # gpu__time_duration.sum of the same capture: ONE launch, cold, serialised by the profiler
+NCU_ISOLATED_US = 70.62  # gpu__time_duration.sum of the same capture: ONE launch, cold, serialised by the profiler
 
 LOSS_CFG = dict(B=8, C=2, S=(128, 128, 128), M=600, grad_scale=65536.0)
 VOTE_CFG = dict(T_global=100, N=30, S=(128, 128, 128))
@@ -993,7 +993,7 @@ def run_loss_workload(args, device, rank, world, local_rank, dist, numa):
                          "frac_isolated": alg_bytes / (NCU_ISOLATED_US * 1e-6) / 1e9 / peak,
                          "overlap": "avg_launch_us is the steady-state time per launch of K back-to-back launches: the ramp of "
                                     "launch k+1 (scheduling, prologue, first loads) runs under the tail of launch k -- programmatic "
-                                    "dependent launch, DS_LOSS_PDL=0 switches it off (66.7 us per step then).  One launch alone "
+                                    "dependent launch, DS_LOSS_PDL=0 switches it off (66.8 us per step then).  One launch alone "
                                     "takes isolated_launch_us_ncu (gpu__time_duration of the ncu capture in traffic_source)",
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "numa": numa,
