@@ -174,6 +174,8 @@ struct VoteParams {
   int64_t units;   // V / VPT
   int chunks;      // CTAs per target
   int raw;         // weights are raw data parameters -> softmax in kernel
+  int64_t tpt;     // staged kernel: tiles (kThreads units) per target
+  int run;         // staged kernel: consecutive tiles a CTA takes before it strides by the grid
 };
 
 // softmax statistics of the N data parameters of target t: row max and 1/sum(exp(x - max)),
@@ -374,6 +376,290 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Staged variant for uint8 label planes (1 B per voxel-candidate).
+//
+// With LDG the uint8 vote is latency-bound: a warp alternates "16 loads -> wait -> ~900 vote instructions", 128
+// registers allow two CTAs per SM, and the bytes in flight collapse whenever the warps vote (0.74-0.81 of HBM,
+// 23 % warps active, 44 % issue-active in profiles/r02_vote_u8_ncu_summary.txt).  Here a producer warp streams
+// the planes into a ring of shared-memory stages with 1-D bulk copies (TMA engine, completion on an mbarrier), so
+// kStgStages - 1 stages of kStgKB planes x 4 KB are in flight per CTA whatever the eight voting warps are doing,
+// and those only ever read shared memory.
+//
+//   tile   = kThreads x 16 consecutive voxels of one target (one 16-byte piece per thread and plane)
+//   stage  = kStgKB candidate planes of one tile (the last stage of a tile holds N mod kStgKB planes)
+//   full[s]: 1 arrival (expect_tx) + bytes;  empty[s]: kWarps arrivals (a warp arrives once it has voted the stage)
+//
+// Persistent grid, one CTA per resident slot; CTA c takes runs c, c + G, c + 2G ... of `run` consecutive tiles, so
+// the grid advances through memory as one front.  The weights of a target are formed per WARP (no CTA-wide barrier
+// anywhere in the loop) with exactly the arithmetic of softmax_stats / fill above, and the vote itself is the same
+// instruction sequence in the same order as vote_kernel: both kernels return identical bits.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef DS_VOTE_STG_KB
+#define DS_VOTE_STG_KB 8
+#endif
+#ifndef DS_VOTE_STG_STAGES
+#define DS_VOTE_STG_STAGES 3
+#endif
+#ifndef DS_VOTE_STG_MINB
+#define DS_VOTE_STG_MINB 2
+#endif
+#ifndef DS_VOTE_STG_EVICT
+#define DS_VOTE_STG_EVICT 1  // L2 evict-first hint on the bulk copies (read-once stream): 135.6 -> 132.7 us on the 13-target shard
+#endif
+constexpr int kStgKB = DS_VOTE_STG_KB;          // divides 16 (ATen cascade blocks)
+constexpr int kStgStages = DS_VOTE_STG_STAGES;
+constexpr int kStgMaxN = 256;                   // per-warp weight rows in shared memory; N < kStgMaxN on this path
+constexpr int kStgTileBytes = kThreads * 16;
+constexpr int kStgStageBytes = kStgKB * kStgTileBytes;
+constexpr int kStgThreads = kThreads + 32;      // eight voting warps + the producer warp
+static_assert(16 % kStgKB == 0, "stage depth must divide the cascade block");
+
+// weights of target t for this warp, bit-identical to softmax_stats + fill for N <= 256
+__device__ __forceinline__ void warp_weights(const VoteParams& p, int64_t t, float* wv, bool ties, double& wtot) {
+  const int lane = threadIdx.x & 31;
+  const int N = (int)p.N;
+  const float* __restrict__ wrow = p.weights + t * p.N;
+  float mx = 0.f, inv = 1.f;
+  if (p.raw) {
+    float m = -INFINITY;
+    for (int n = lane; n < N; n += 32) m = fmaxf(m, __ldg(wrow + n));
+    mx = warp_max(m);
+    float s = 0.f;
+    for (int n0 = 0; n0 < N; n0 += 32) {  // the partial sums of the 256-thread layout: one "warp" per 32 candidates
+      const int n = n0 + lane;
+      s += warp_sum(n < N ? expf(__ldg(wrow + n) - mx) : 0.f);
+    }
+    inv = 1.0f / s;
+  }
+  for (int n = lane; n < N; n += 32) {
+    const float x = __ldg(wrow + n);
+    wv[n] = p.raw ? expf(x - mx) * inv : x;
+  }
+  __syncwarp();
+  if (ties) {
+    double a = 0.0;
+    if (lane == 0)
+      for (int i = 0; i < N; ++i) a += (double)wv[i];
+    wtot = __shfl_sync(0xffffffffu, a, 0);
+  }
+}
+
+template <typename OT, int LEVELS, bool TIES>
+__global__ void __launch_bounds__(kStgThreads, DS_VOTE_STG_MINB) vote_kernel_u8_staged(const VoteParams p) {
+  using In = VoteIn<uint8_t, true>;
+  constexpr int VPT = 16;
+  static_assert(In::VPT == VPT, "the staged vote moves 16 voxels per thread and plane");
+  extern __shared__ __align__(128) unsigned char s_ring[];  // kStgStages x kStgStageBytes
+  __shared__ __align__(8) uint64_t s_full[kStgStages], s_empty[kStgStages];
+  __shared__ float s_wv[kWarps][kStgMaxN];
+  __shared__ unsigned int s_ties;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t N = p.N, V = p.V, tpt = p.tpt, units = p.units;
+  const int64_t total = p.T * tpt, R = p.run, stride = (int64_t)gridDim.x * R;
+  const int groups = (int)((N + kStgKB - 1) / kStgKB);
+  const uint8_t* __restrict__ lab = reinterpret_cast<const uint8_t*>(p.labels);
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStgStages; ++s) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], kWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    s_ties = 0u;
+  }
+  __syncthreads();
+
+  unsigned int my_ties = 0u;
+  if (warp == kWarps) {
+    // ---- producer: one thread walks the CTA's (tile, stage) sequence ----
+    if (lane == 0) {
+      int s = 0;
+      unsigned round = 0u;
+#if DS_VOTE_STG_EVICT
+      const uint64_t policy = l2_policy_evict_first();
+#endif
+      for (int64_t run0 = (int64_t)blockIdx.x * R; run0 < total; run0 += stride) {
+        const int64_t run1 = run0 + R < total ? run0 + R : total;
+        for (int64_t tile = run0; tile < run1; ++tile) {
+          const int64_t t = tile / tpt, u0 = (tile - t * tpt) * kThreads;
+          const unsigned bytes = (unsigned)((units - u0 < kThreads ? units - u0 : kThreads) * VPT);
+          const uint8_t* src = lab + t * N * V + u0 * VPT;
+          for (int g = 0; g < groups; ++g) {
+            const int n0 = g * kStgKB;
+            const int cnt = (int)(N - n0 < kStgKB ? N - n0 : kStgKB);
+            if (round > 0u) mbar_wait(&s_empty[s], (round - 1u) & 1u);
+            mbar_expect_tx(&s_full[s], (unsigned)cnt * bytes);
+            unsigned char* st = s_ring + (size_t)s * kStgStageBytes;
+            for (int j = 0; j < cnt; ++j) {
+#if DS_VOTE_STG_EVICT
+              tma_load_1d_hint(st + j * kStgTileBytes, src + (int64_t)(n0 + j) * V, bytes, &s_full[s], policy);
+#else
+              tma_load_1d(st + j * kStgTileBytes, src + (int64_t)(n0 + j) * V, bytes, &s_full[s]);
+#endif
+            }
+            if (++s == kStgStages) s = 0, ++round;
+          }
+        }
+      }
+    }
+  } else {
+    // ---- voting warps ----
+    float* wv = s_wv[warp];
+    int64_t cur_t = -1;
+    double wtot = 0.0;
+    int s = 0;
+    unsigned phase = 0u;
+    for (int64_t run0 = (int64_t)blockIdx.x * R; run0 < total; run0 += stride) {
+      const int64_t run1 = run0 + R < total ? run0 + R : total;
+      for (int64_t tile = run0; tile < run1; ++tile) {
+        const int64_t t = tile / tpt, u0 = (tile - t * tpt) * kThreads;
+        const int64_t u = u0 + threadIdx.x;
+        const bool active = u < units;
+        if (t != cur_t) {
+          __syncwarp();  // every lane is done with the previous target's weights
+          warp_weights(p, t, wv, TIES, wtot);
+          cur_t = t;
+        }
+        float acc[LEVELS][VPT];
+#pragma unroll
+        for (int l = 0; l < LEVELS; ++l)
+#pragma unroll
+          for (int i = 0; i < VPT; ++i) acc[l][i] = 0.f;
+
+        for (int g = 0; g < groups; ++g) {
+          const int n0 = g * kStgKB;
+          const int cnt = (int)(N - n0 < kStgKB ? N - n0 : kStgKB);
+          mbar_wait(&s_full[s], phase);
+          const unsigned char* st = s_ring + (size_t)s * kStgStageBytes + threadIdx.x * VPT;
+          auto batch = [&](auto bn_tag, int jb) {  // planes jb .. jb + BN - 1 of this stage
+            constexpr int BN = decltype(bn_tag)::value;
+            typename In::Raw raw[BN];
+#pragma unroll
+            for (int j = 0; j < BN; ++j) {
+              const uint4 v = *reinterpret_cast<const uint4*>(st + (jb + j) * kStgTileBytes);
+              raw[j].w[0] = v.x, raw[j].w[1] = v.y, raw[j].w[2] = v.z, raw[j].w[3] = v.w;
+            }
+            uint32_t nonbin = 0u;
+#pragma unroll
+            for (int j = 0; j < BN; ++j) nonbin |= In::nonbinary_bits(raw[j]);
+            if (nonbin == 0u) {
+#pragma unroll
+              for (int j = 0; j < BN; ++j) In::add_binary(raw[j], wv[n0 + jb + j], acc[0]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN; ++j) {
+                const float w = wv[n0 + jb + j];
+                float f[VPT];
+                In::to_float(raw[j], f);
+#pragma unroll
+                for (int i = 0; i < VPT; ++i) acc[0][i] = __fadd_rn(acc[0][i], __fmul_rn(f[i], w));
+              }
+            }
+          };
+          if (active) {
+            if (cnt == kStgKB) {
+              batch(std::integral_constant<int, kStgKB>{}, 0);
+            } else {
+              int jb = 0;
+              if constexpr (kStgKB > 8) {
+                if (cnt - jb >= 8) batch(std::integral_constant<int, 8>{}, jb), jb += 8;
+              }
+              if constexpr (kStgKB > 4) {
+                if (cnt - jb >= 4) batch(std::integral_constant<int, 4>{}, jb), jb += 4;
+              }
+              if constexpr (kStgKB > 2) {
+                if (cnt - jb >= 2) batch(std::integral_constant<int, 2>{}, jb), jb += 2;
+              }
+              if (cnt - jb >= 1) batch(std::integral_constant<int, 1>{}, jb);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[s]);  // this warp has voted the stage
+          if (++s == kStgStages) s = 0, phase ^= 1u;
+          if constexpr (LEVELS > 1) {  // ATen cascade, as in vote_kernel
+            const int done = n0 + cnt;
+            if (cnt == kStgKB && (done & 15) == 0) {
+#pragma unroll
+              for (int i = 0; i < VPT; ++i) acc[1][i] = __fadd_rn(acc[1][i], acc[0][i]), acc[0][i] = 0.f;
+              if constexpr (LEVELS > 2) {
+                if ((done & 255) == 0) {
+#pragma unroll
+                  for (int i = 0; i < VPT; ++i) acc[2][i] = __fadd_rn(acc[2][i], acc[1][i]), acc[1][i] = 0.f;
+                }
+              }
+            }
+          }
+        }
+        if (active) {
+          bool on[VPT];
+#pragma unroll
+          for (int i = 0; i < VPT; ++i) {
+            float sum = acc[0][i];
+#pragma unroll
+            for (int l = 1; l < LEVELS; ++l) sum = __fadd_rn(sum, acc[l][i]);
+            on[i] = sum > 0.5f;
+            if (TIES) {
+              const double fg = (double)sum, bg = wtot - fg;
+              const double top = fg > bg ? fg : bg;
+              my_ties += (fabs(fg - bg) < 1e-6 * top) ? 1u : 0u;
+            }
+          }
+          store_labels<OT, VPT>(reinterpret_cast<OT*>(p.out) + t * V + u * VPT, on);
+        }
+      }
+    }
+  }
+  __threadfence();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (TIES) {
+    my_ties = (unsigned int)warp_sum((int)my_ties);
+    if (lane == 0 && my_ties) atomicAdd(&s_ties, my_ties);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_ties) atomicAdd(p.near_ties, (unsigned long long)s_ties);
+  }
+}
+
+// uint8 planes, many tiles per resident CTA, N <= 256, 16-byte aligned rows: the staged kernel
+template <typename OT>
+int launch_vote_staged(const VoteParams& p0, cudaStream_t stream) {
+  VoteParams p = p0;
+  p.units = p.V / 16;
+  p.tpt = (p.units + kThreads - 1) / kThreads;
+  const bool ties = p.near_ties != nullptr;
+  const int levels = p.N < 16 ? 1 : 2;  // N < 256: level 1 is never folded
+  void (*kern)(const VoteParams) = nullptr;
+  if (levels == 1) kern = ties ? vote_kernel_u8_staged<OT, 1, true> : vote_kernel_u8_staged<OT, 1, false>;
+  else kern = ties ? vote_kernel_u8_staged<OT, 2, true> : vote_kernel_u8_staged<OT, 2, false>;
+  const size_t smem = (size_t)kStgStages * kStgStageBytes;
+  static thread_local void (*occ_kern)(const VoteParams) = nullptr;
+  static thread_local int occ_cached = 0;
+  if (occ_kern != kern) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return fail(DS_ERR_ARG, "ds_consensus_vote: %zu bytes of shared memory refused", smem);
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kStgThreads, smem) != cudaSuccess || o < 1) o = 1;
+    occ_kern = kern, occ_cached = o;
+  }
+  p.run = env_int("DS_VOTE_STG_RUN", 2);
+  if (p.run < 1) p.run = 1;
+  const int64_t total = p.T * p.tpt, runs = (total + p.run - 1) / p.run;
+  int64_t grid = (int64_t)sm_count() * occ_cached;
+  if (grid > runs) grid = runs;
+  static const bool pdl = env_int("DS_VOTE_PDL", 1) != 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(kStgThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, p);
+  count_launch();
+  return check_launch("ds_consensus_vote");
+}
+
 template <typename LT, typename OT, bool VECP>
 int launch_vote(const VoteParams& p0, cudaStream_t stream) {
   VoteParams p = p0;
@@ -486,5 +772,11 @@ extern "C" int ds_consensus_vote(const void* labels, int label_dtype, const floa
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (label_dtype == DS_I64)
     return out_dtype == DS_I64 ? dispatch_align<int64_t, int64_t>(p, s) : dispatch_align<int64_t, uint8_t>(p, s);
+  // uint8 planes with enough tiles to keep a persistent grid busy: the staged (bulk-copy) kernel
+  const int64_t tiles = T * ((V / 16 + kThreads - 1) / kThreads);
+  const bool staged = env_int("DS_VOTE_STAGED", 1) && V % 16 == 0 && N < kStgMaxN &&
+                      reinterpret_cast<uintptr_t>(labels) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                      tiles >= (int64_t)env_int("DS_VOTE_STG_MIN_TILES", 8) * 2 * sm_count();
+  if (staged) return out_dtype == DS_I64 ? launch_vote_staged<int64_t>(p, s) : launch_vote_staged<uint8_t>(p, s);
   return out_dtype == DS_I64 ? dispatch_align<uint8_t, int64_t>(p, s) : dispatch_align<uint8_t, uint8_t>(p, s);
 }

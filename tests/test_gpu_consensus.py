@@ -226,3 +226,81 @@ def test_invalid_arguments_raise(cuda_device):
         ds.calc_dp_consensus([torch.zeros((2, 2, 2), dtype=torch.long, device=cuda_device)], [0.1, 0.2])
     with pytest.raises(RuntimeError):
         ds.consensus_batched(torch.zeros((1, 2, 4), dtype=torch.long), torch.zeros((1, 2)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# staged (bulk-copy) uint8 vote kernel: forced at small sizes through DS_VOTE_STG_MIN_TILES=0
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def force_staged(monkeypatch):
+    monkeypatch.setenv("DS_VOTE_STG_MIN_TILES", "0")
+    monkeypatch.setenv("DS_VOTE_STAGED", "1")
+    return monkeypatch
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 15, 16, 17, 30, 32, 33, 64, 255, 256])
+@pytest.mark.parametrize("shape", [(6, 8, 16), (17, 16, 16), (4, 32, 64)])
+def test_staged_u8_vote_vs_oracle_and_ldg_kernel(cuda_device, force_staged, n, shape):
+    """every candidate count around the stage depth (8) and the ATen cascade block (16), tiles that are ragged
+    (768 and 4352 voxels: a partial 4096-voxel tile) and exact (8192); N >= 256 falls back to the LDG kernel"""
+    import deep_staple_b200 as ds
+
+    gen = torch.Generator().manual_seed(500 + n)
+    T = 3
+    labels = (torch.rand((T, n, *shape), generator=gen) < 0.45).to(torch.uint8)
+    dps = 0.7 * torch.randn((T, n), generator=gen)
+    lab_d, dps_d = labels.to(cuda_device), dps.to(cuda_device)
+    out, ties = ds.consensus_batched(lab_d, dps_d, count_near_ties=True)
+    out64 = ds.consensus_batched(lab_d, dps_d, out_dtype=torch.int64)
+    assert out.dtype == torch.uint8 and out64.dtype == torch.int64
+    assert torch.equal(out.long(), out64)
+    force_staged.setenv("DS_VOTE_STAGED", "0")
+    ref_k, ref_ties = ds.consensus_batched(lab_d, dps_d, count_near_ties=True)
+    assert torch.equal(out, ref_k), "staged and LDG vote kernels must return identical bits"
+    assert int(ties) == int(ref_ties)
+    for t in range(T):
+        lb = [labels[t, i].long() for i in range(n)]
+        ref = oc.calc_dp_consensus(lb, [float(x) for x in dps[t]])
+        _compare(out[t], ref, lb, [float(x) for x in dps[t]], f"staged N={n}/{shape}/t{t}")
+
+
+def test_staged_u8_vote_label_values_above_one_and_presoftmaxed(cuda_device, force_staged):
+    import deep_staple_b200 as ds
+
+    gen = torch.Generator().manual_seed(31)
+    labels = torch.randint(0, 4, (2, 13, 8, 16, 16), generator=gen).to(torch.uint8)
+    labels[1, :, :4] = (labels[1, :, :4] > 1).to(torch.uint8)  # a binary region next to a multi-valued one
+    dps = torch.randn((2, 13), generator=gen)
+    w = torch.softmax(dps, 1)
+    out = ds.consensus_batched(labels.to(cuda_device), dps.to(cuda_device))
+    out_w = ds.consensus_batched(labels.to(cuda_device), w.to(cuda_device), weights_are_softmaxed=True)
+    force_staged.setenv("DS_VOTE_STAGED", "0")
+    assert torch.equal(out, ds.consensus_batched(labels.to(cuda_device), dps.to(cuda_device)))
+    assert torch.equal(out_w, ds.consensus_batched(labels.to(cuda_device), w.to(cuda_device), weights_are_softmaxed=True))
+    for t in range(2):
+        lb, d = [l.long() for l in labels[t]], [float(x) for x in dps[t]]
+        ref = oc.calc_dp_consensus(lb, d)
+        s64, _ = oc.vote_sums(lb, d, torch.float64)
+        safe = (s64 - 0.5).abs() > 1e-6
+        assert torch.equal(out[t].long().cpu()[safe], ref[safe])
+        assert torch.equal(out_w[t].long().cpu()[safe], ref[safe])
+
+
+def test_staged_u8_vote_cfg3_shard_identical_to_ldg_kernel(cuda_device, monkeypatch):
+    """cfg3's per-GPU shard at 8 GPUs (13 targets x 30 candidates x 128^3, uint8): the size at which the staged
+    kernel is selected on its own; bits equal to the LDG kernel's, one target against the oracle"""
+    import deep_staple_b200 as ds
+
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    T, N, S = 13, 30, (128, 128, 128)
+    labels = (torch.rand((T, N, *S), generator=gen, device=cuda_device) < 0.35).to(torch.uint8)
+    dps = 2 * torch.randn((T, N), generator=gen, device=cuda_device)
+    n0 = ds.launch_count()
+    out, ties = ds.consensus_batched(labels, dps, count_near_ties=True)
+    assert ds.launch_count() == n0 + 1
+    monkeypatch.setenv("DS_VOTE_STAGED", "0")
+    ref_k, ref_ties = ds.consensus_batched(labels, dps, count_near_ties=True)
+    assert torch.equal(out, ref_k) and int(ties) == int(ref_ties)
+    lb = [labels[12, i].long().cpu() for i in range(N)]
+    d = [float(x) for x in dps[12].cpu()]
+    _compare(out[12], oc.calc_dp_consensus(lb, d), lb, d, "staged cfg3 shard/t12")
