@@ -15,6 +15,7 @@ from .consensus import (  # noqa: F401
     group_snapshot,
     staple_batched,
 )
+from .host_io import LabelUploader, narrow_labels_host  # noqa: F401
 from .loss import (  # noqa: F401
     DPLossOutput,
     backward_logits,

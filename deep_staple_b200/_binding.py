@@ -69,6 +69,7 @@ SIGNATURES = {
                                            c_double, c_int, c_void_p]),
     "ds_label_stats": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                c_size_t, c_void_p]),
+    "ds_host_narrow_labels": (c_int, [c_void_p, c_void_p, c_int64, c_int]),
 }
 
 _lib = None

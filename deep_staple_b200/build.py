@@ -38,7 +38,7 @@ def _nvcc() -> str:
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def _fingerprint() -> str:
@@ -58,8 +58,26 @@ def is_current() -> bool:
         return fh.read().strip() == _fingerprint()
 
 
-def _compile(src: str, verbose: bool) -> str:
-    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+def _headers_digest() -> str:
+    h = hashlib.sha256()
+    for path in sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc"))
+                       + [os.path.join(INCLUDE, "deep_staple_b200.h")]):
+        with open(path, "rb") as fh:
+            h.update(os.path.basename(path).encode() + b"\0" + fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src: str, verbose: bool, headers: str = "") -> str:
+    """One translation unit -> build/obj/<name>.o; skipped when source, headers and flags are unchanged."""
+    obj = os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
+    with open(src, "rb") as fh:
+        key = hashlib.sha256(fh.read() + headers.encode()).hexdigest()
+    stamp = obj + ".stamp"
+    if headers and not verbose and os.path.exists(obj) and os.path.exists(stamp):
+        with open(stamp) as fh:
+            if fh.read().strip() == key:
+                return obj
     cmd = [_nvcc(), *NVCC_FLAGS, *INCLUDE_FLAGS, "-c", src, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas")
@@ -69,6 +87,8 @@ def _compile(src: str, verbose: bool) -> str:
         raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
     if verbose:
         sys.stderr.write(res.stderr)
+    with open(stamp, "w") as fh:
+        fh.write(key)
     return obj
 
 
@@ -80,7 +100,7 @@ def build_variant(name: str, extra_flags) -> str:
     objs = []
 
     def one(src):
-        obj = os.path.join(out_dir, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(out_dir, os.path.splitext(os.path.basename(src))[0] + ".o")
         res = subprocess.run([_nvcc(), *NVCC_FLAGS, *extra_flags, *INCLUDE_FLAGS, "-c", src, "-o", obj],
                              capture_output=True, text=True)
         if res.returncode != 0:
@@ -107,7 +127,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     srcs = sources()
     with cf.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as pool:
-        objs = list(pool.map(lambda s: _compile(s, verbose), srcs))
+        headers = "" if force else _headers_digest()
+        objs = list(pool.map(lambda s: _compile(s, verbose, headers), srcs))
     cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

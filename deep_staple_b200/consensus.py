@@ -154,6 +154,43 @@ def consensus_sparse(
     return (out, ties) if count_near_ties else out
 
 
+_host_staging = {}  # one pinned staging buffer (the last size used) + the event of the copy that last read it
+
+
+def _upload_host_candidates(lbls, dev) -> Optional[torch.Tensor]:
+    """Dense int64 candidate volumes in HOST memory (the notebook's ``DEVICE='cpu'``, consensus.ipynb:30, 382-392)
+    -> ``[1, N, *S]`` uint8 on ``dev``: each volume is packed to one byte per voxel by ``ds_host_narrow_labels``
+    straight into a pinned staging buffer and the stack crosses PCIe in ONE copy of N x V bytes (instead of N copies
+    of 8 V bytes plus a device-side ``torch.stack``).  Returns None when the fast path does not apply (device
+    inputs, other dtypes, labels above 255): the caller then uploads the volumes as they are."""
+    from .host_io import narrow_labels_host
+
+    if any(l.is_cuda or l.dtype != torch.int64 or l.shape != lbls[0].shape for l in lbls):
+        return None
+    n, v = len(lbls), lbls[0].numel()
+    if v == 0:
+        return None
+    slot = _host_staging.get("slot")
+    if slot is None or slot[0].numel() < n * v:
+        _host_staging.clear()
+        slot = [torch.empty(n * v, dtype=torch.uint8).pin_memory(), None]
+        _host_staging["slot"] = slot
+    if slot[1] is not None:
+        slot[1].synchronize()
+    staging = slot[0][: n * v].view(n, v)
+    try:
+        for i, l in enumerate(lbls):
+            narrow_labels_host(l, staging[i])
+    except ValueError:
+        return None  # a label above 255: not this path
+    with torch.cuda.device(dev):
+        out = torch.empty((1, n, *lbls[0].shape), dtype=torch.uint8, device=dev)
+        out.view(n, v).copy_(staging, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(dev))
+    return out
+
+
 def calc_dp_consensus(lbl_list: Sequence[torch.Tensor], weighting_list, *, device=None, return_near_ties: bool = False):
     """Drop-in for the reference's ``calc_dp_consensus`` (consensus.ipynb:100-109): fuse N registered
     label candidates of one target by the softmax of their data parameters and threshold the vote
@@ -172,7 +209,9 @@ def calc_dp_consensus(lbl_list: Sequence[torch.Tensor], weighting_list, *, devic
             lbls = [l.long() for l in lbls]
         if lbls[0].dtype not in (torch.int64, torch.uint8):
             lbls = [l.long() for l in lbls]
-        stack = torch.stack([l.to(dev, non_blocking=True) for l in lbls]).unsqueeze(0)  # [1, N, *S]
+        stack = _upload_host_candidates(lbls, dev)  # int64 volumes in host memory: packed to uint8, one copy
+        if stack is None:
+            stack = torch.stack([l.to(dev, non_blocking=True) for l in lbls]).unsqueeze(0)  # [1, N, *S]
         w = _weights_tensor(weighting_list, dev)
         if w.numel() != len(lbls):
             raise ValueError(f"{len(lbls)} label candidates but {w.numel()} weights")

@@ -321,6 +321,17 @@ int ds_label_stats(const void* pred, int pred_dtype, const void* target, int tar
                    int64_t C, int64_t V, double* inst_stats, void* workspace, size_t workspace_bytes,
                    ds_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host-side label packer of the upload path (runs on the HOST, no device needed)
+ *   replaces  b_seg_modified.to(device=config.device)            main_deep_staple.py:687
+ *             and the dense int64 candidate uploads of            consensus.ipynb:382-392
+ * Packs n int64 labels (class indices < 256) to uint8 with `threads` worker threads (<= 0: all
+ * hardware threads) so that 1 byte per voxel instead of 8 crosses PCIe; every kernel above reads
+ * DS_U8 labels natively.  dst is typically a pinned staging buffer.  Lossless: returns DS_ERR_ARG
+ * (dst unspecified) if any label lies outside [0, 255] -- the caller then uploads the int64 labels.
+ * ------------------------------------------------------------------------------------------- */
+int ds_host_narrow_labels(const int64_t* src, uint8_t* dst, int64_t n, int threads);
+
 #ifdef __cplusplus
 }
 #endif
