@@ -33,7 +33,7 @@ int setup_tiles(LossParams& p, const char* who, bool stats) {
   p.steps_per_inst = (p.units + 31) / 32;
   p.n_steps = p.steps_per_inst * p.B_local;
   int per_sm = env_int("DS_LOSS_CTAS_PER_SM", loss_min_blocks(p.units == p.V ? 0 : p.C, p.units * 8 == p.V ? 8 : 4));
-  if (p.use_tma) per_sm = env_int("DS_LOSS_TMA_CTAS_PER_SM", kTmaMinBlocks);
+  if (p.use_tma) per_sm = env_int("DS_LOSS_TMA_CTAS_PER_SM", p.tma_min_blocks);
   int64_t grid = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
   const int64_t need = (p.n_steps + kWarps - 1) / kWarps;
   if (grid > need) grid = need;
@@ -70,7 +70,7 @@ int setup_tiles(LossParams& p, const char* who, bool stats) {
       // 211.8 vs 210.1 us) -- two CTAs per SM drift less than four, and the claim sits on the producer's path.
       const int64_t tiles = (p.units + kThreads - 1) / kThreads, tile_rounds = tiles / (p.grid / groups);
       const int64_t k_static = tile_rounds * env_int("DS_LOSS_TMA_STATIC_PCT", 100) / 100;
-      if (groups == p.B_local && tile_rounds >= 6 && k_static >= kTmaStages - 1 && k_static < tile_rounds)
+      if (groups == p.B_local && tile_rounds >= 6 && k_static >= p.tma_stages - 1 && k_static < tile_rounds)
         p.dyn_static = (unsigned)k_static;
       else
         p.claims = nullptr;
@@ -110,8 +110,10 @@ int setup_geometry(LossParams& p, int logit_dtype, int target_dtype, bool* vec_o
   // else LDG: fp32 C = 2 68 vs 74, any forward-only C = 2 launch (fp16 37 vs 43, fp32 45 vs 53, uint8 labels 38
   // vs 51), uint8 labels with gradients (57.4 vs 57.6, fp16 42 vs 45), half logits with C = 3 (209 vs 255: eight
   // voxels x three planes per thread cost the TMA shell its registers).  DS_LOSS_TMA=0/1 overrides.
+  const TmaShape shape = tma_shape(logit_dtype == DS_F32 ? 4 : 2, C);
+  p.tma_stages = shape.stages, p.tma_min_blocks = shape.min_blocks;
   const bool eligible = vec && stats && !p.dice_target && C >= 2 && C <= 4 && (p.V % 16 == 0) &&
-                        p.B_local <= (int64_t)sm_count() * env_int("DS_LOSS_TMA_CTAS_PER_SM", kTmaMinBlocks);
+                        p.B_local <= (int64_t)sm_count() * env_int("DS_LOSS_TMA_CTAS_PER_SM", p.tma_min_blocks);
   const bool heavy = C == 2 && logit_dtype != DS_F32 && target_dtype == DS_I64 && p.dlogits != nullptr;
   const int choice = env_int("DS_LOSS_TMA", -1);
   p.use_tma = eligible && (choice < 0 ? heavy : choice != 0);

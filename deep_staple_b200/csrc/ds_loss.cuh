@@ -79,6 +79,7 @@ struct LossParams {
   double nll_scale;             // fixed-point scale of the loss sums (power of two)
   int C, use_risk, mode, finalize, dp_outputs, grid, groups;
   int use_tma;                           // launch the TMA-staged shell (ds_loss_tma.cuh)
+  int tma_stages, tma_min_blocks;        // its ring depth and resident CTAs per SM for this variant (host side only)
   const double* stats_smem;              // device-side only: statistics staged in shared memory for the epilogue
   // fused multi-GPU exchange (ds_dp_loss_fwd_bwd_exchange): peer-mapped exchange buffers, see finish_launch
   const unsigned long long* peer_bases;  // device array [world]: base address of every rank's exchange buffer

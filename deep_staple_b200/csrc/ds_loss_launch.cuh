@@ -31,7 +31,7 @@ int launch_cfg(const LossParams& p, bool grad, bool stats, cudaStream_t stream) 
   const bool dice = stats && p.dice_target != nullptr;
   if constexpr (C >= 2 && C <= 4 && VEC > 1) {
     if (p.use_tma && stats && !dice) {
-      constexpr int smem = kTmaStages * tma_stage_bytes<LT, TT, C, VEC>();
+      constexpr int smem = tma_shape((int)sizeof(LT), C).stages * tma_stage_bytes<LT, TT, C, VEC>();
       auto launch = [&](auto kernel) -> int {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail((int)e, "loss_kernel_tma: %s", cudaGetErrorString(e));

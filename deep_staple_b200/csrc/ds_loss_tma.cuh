@@ -31,6 +31,17 @@ namespace ds {
 constexpr int kTmaStages = DS_TMA_STAGES;
 constexpr int kTmaMinBlocks = DS_TMA_MIN_BLOCKS;
 
+// Ring depth and resident CTAs per SM of a variant.  Default: 4 stages x 2 CTAs.  Half-precision logits with two
+// classes (a 24.6 KB stage with int64 labels, 80 registers without spills): 2 stages x 3 CTAs -- the variant is bound by
+// instruction issue as much as by bytes and 24 resident warps hide more of it than 16 (cfg2 fp16 fwd+bwd 48.0 -> 45.9 us,
+// profiles/r02_notes/half_shell_ab.log; with three classes the third CTA costs spills: 179 -> 193 us, so that stays).
+struct TmaShape {
+  int stages, min_blocks;
+};
+__host__ __device__ constexpr TmaShape tma_shape(int logit_bytes, int C) {
+  return (logit_bytes == 2 && C == 2) ? TmaShape{2, 3} : TmaShape{kTmaStages, kTmaMinBlocks};
+}
+
 template <int BYTES>
 __device__ __forceinline__ void lds_raw(const void* p, Raw<BYTES>& r) {
   if constexpr (BYTES % 16 == 0) {
@@ -56,7 +67,8 @@ constexpr int tma_stage_bytes() {
 // C in {2, 3, 4}; vector path only (V % VEC == 0, and V % 16 == 0 for uint8 labels so that every bulk
 // copy is a multiple of 16 bytes); no separate Dice target.
 template <typename LT, typename TT, int C, int VEC, bool GRAD>
-__global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const LossParams p) {
+__global__ void __launch_bounds__(kThreads, tma_shape((int)sizeof(LT), C).min_blocks) loss_kernel_tma(const LossParams p) {
+  constexpr int kStages = tma_shape((int)sizeof(LT), C).stages;
   constexpr int CC = C;
   constexpr bool STATS = true, DICE = false;
   constexpr int nc = C;
@@ -64,9 +76,9 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   constexpr int kPlaneBytes = kTileV * (int)sizeof(LT);
   constexpr int kLabelBytes = kTileV * (int)sizeof(TT);
   constexpr int kStageBytes = C * kPlaneBytes + kLabelBytes;
-  extern __shared__ __align__(128) unsigned char s_ring[];  // kTmaStages x kStageBytes
-  __shared__ __align__(8) uint64_t s_full[kTmaStages], s_empty[kTmaStages];
-  __shared__ int s_tile[kTmaStages];
+  extern __shared__ __align__(128) unsigned char s_ring[];  // kStages x kStageBytes
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+  __shared__ int s_tile[kStages];
   __shared__ double s_scratch[kWarps + 1];
 
   __shared__ EpiShared s_epi;
@@ -92,15 +104,15 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   // address order keeps the front narrow.  s_tile[stage] carries the tile index to the consumers; -1 ends.
   const bool dynamic = p.claims != nullptr;
   unsigned int* ctr = dynamic ? p.claims + (size_t)b * kWarps * kTicketStride : nullptr;
-  const int64_t k_static = dynamic ? (int64_t)p.dyn_static : 0;  // static rounds (>= kTmaStages - 1, host)
+  const int64_t k_static = dynamic ? (int64_t)p.dyn_static : 0;  // static rounds (>= kStages - 1, host)
   const int64_t dyn_base = k_static * per_group;
   unsigned pending = 0u;      // producer thread: ticket claimed for the next dynamic tile
   bool prod_done = false;     // producer thread: the instance has no tiles left
 
-  // producer side (thread 0): fill stage (k % kTmaStages) with this CTA's k-th tile
+  // producer side (thread 0): fill stage (k % kStages) with this CTA's k-th tile
   auto produce = [&](int64_t k) {
-    const int s = (int)(k % kTmaStages);
-    const unsigned round = (unsigned)(k / kTmaStages);
+    const int s = (int)(k % kStages);
+    const unsigned round = (unsigned)(k / kStages);
     int64_t ti = (int64_t)j0 + k * per_group;
     if (dynamic && k >= k_static) {
       ti = dyn_base + (int64_t)pending;
@@ -129,11 +141,11 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   if (dynamic) pdl_wait_for_previous_grid();  // the claim counters live in the workspace
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], kWarps);
+    for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], kWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (dynamic) pending = atomicAdd(ctr, 1u);
-    for (int64_t k = 0; k < kTmaStages - 1 && !prod_done; ++k) produce(k);
+    for (int64_t k = 0; k < kStages - 1 && !prod_done; ++k) produce(k);
   }
   const double g = (GRAD && p.grad_scale) ? (double)__ldg(p.grad_scale) : 1.0;
   const float gV = (float)g / (float)V;
@@ -197,9 +209,9 @@ __global__ void __launch_bounds__(kThreads, kTmaMinBlocks) loss_kernel_tma(const
   };
 
   for (int64_t k = 0;; ++k) {
-    if (threadIdx.x == 0 && !prod_done) produce(k + kTmaStages - 1);
-    const int s = (int)(k % kTmaStages);
-    mbar_wait(&s_full[s], (unsigned)(k / kTmaStages) & 1u);
+    if (threadIdx.x == 0 && !prod_done) produce(k + kStages - 1);
+    const int s = (int)(k % kStages);
+    mbar_wait(&s_full[s], (unsigned)(k / kStages) & 1u);
     const int ti = s_tile[s];
     if (ti < 0) break;
     const int64_t v = (int64_t)ti * kTileV + (int64_t)threadIdx.x * VEC;

@@ -19,12 +19,18 @@ _MAX_THREADS = 16
 
 
 def default_threads() -> int:
-    """Worker threads of the packer: the CPUs this process may run on (its NUMA binding), at most 16."""
+    """Worker threads of the packer: the CPUs this process may run on (its NUMA binding), at most 16, and no more
+    than this rank's share of the machine when several ranks run on it (torchrun's LOCAL_WORLD_SIZE)."""
     try:
         n = len(os.sched_getaffinity(0))
     except AttributeError:  # pragma: no cover
         n = os.cpu_count() or 1
-    return max(1, min(n, _MAX_THREADS))
+    try:
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except ValueError:
+        local_world = 1
+    share = max(1, (os.cpu_count() or n) // local_world)
+    return max(1, min(n, share, _MAX_THREADS))
 
 
 def narrow_labels_host(labels: torch.Tensor, out: Optional[torch.Tensor] = None, threads: Optional[int] = None) -> torch.Tensor:
