@@ -875,25 +875,31 @@ def vote_section(device, rank, world, steps, warmup, peak, dist, dtypes=("int64"
         if dist:
             gsteps = max(3, min(steps, 10))
 
-            def gathered():
-                sharded_consensus(labels, dps, c["T_global"], gather=True)
+            def timed_gather(fused):
+                def gathered():
+                    sharded_consensus(labels, dps, c["T_global"], gather=True, fused=fused, out_dtype=torch.uint8)
 
-            for _ in range(2):
-                gathered()
-            torch.cuda.synchronize()
-            dist.barrier()
-            t0 = time.perf_counter()
-            for _ in range(gsteps):
-                gathered()
-            torch.cuda.synchronize()
-            dist.barrier()
-            gsec = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
-            dist.all_reduce(gsec, op=dist.ReduceOp.MAX)
-            gms = float(gsec.item()) / gsteps * 1e3
-            rec["ms_vote_plus_gather"] = gms
-            rec["ms_gather"] = gms - rec["ms_vote"]
-            rec["gather_bytes_received_per_rank"] = (-(-c["T_global"] // world)) * world * V  # uint8 maps travel, widened on arrival
-            rec["gvoxel_candidates_per_s_with_gather"] = c["T_global"] * c["N"] * V / (gms / 1e3) / 1e9
+                for _ in range(2):
+                    gathered()
+                torch.cuda.synchronize()
+                dist.barrier()
+                t0 = time.perf_counter()
+                for _ in range(gsteps):
+                    gathered()
+                torch.cuda.synchronize()
+                dist.barrier()
+                gsec = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+                dist.all_reduce(gsec, op=dist.ReduceOp.MAX)
+                return float(gsec.item()) / gsteps * 1e3
+
+            nccl_ms, fused_ms = timed_gather(False), timed_gather(True)
+            rec["ms_vote_plus_gather"] = fused_ms
+            rec["ms_gather"] = fused_ms - rec["ms_vote"]
+            rec["gather"] = ("inside the vote kernel: every map stored into all ranks' buffers over NVLink peer memory "
+                             "(ds_consensus_vote_gather), two signal-pad barriers, no NCCL call; uint8 maps")
+            rec["ms_vote_plus_nccl_all_gather"] = nccl_ms
+            rec["gather_bytes_received_per_rank"] = c["T_global"] * V  # uint8 maps travel
+            rec["gvoxel_candidates_per_s_with_gather"] = c["T_global"] * c["N"] * V / (fused_ms / 1e3) / 1e9
         out[name] = rec
         del labels, res
         torch.cuda.empty_cache()

@@ -33,6 +33,8 @@ SIGNATURES = {
     "ds_launch_count": (c_uint64, []),
     "ds_consensus_vote": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int,
                                   c_void_p, c_void_p]),
+    "ds_consensus_vote_gather": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                         c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ds_consensus_vote_multiclass": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_int,
                                              c_void_p, c_int, c_void_p]),
     "ds_consensus_vote_sparse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64,

@@ -176,7 +176,23 @@ struct VoteParams {
   int raw;         // weights are raw data parameters -> softmax in kernel
   int64_t tpt;     // staged kernel: tiles (kThreads units) per target
   int run;         // staged kernel: consecutive tiles a CTA takes before it strides by the grid
+  // fused vote + all-gather (ds_consensus_vote_gather): the map of local target t is stored at row t_offset + t of the
+  // [T_global, V] buffer of EVERY rank (peer memory over NVLink / NVSwitch; this rank's own buffer is one of them)
+  void* peers[DS_MAX_PEERS];
+  int n_peers;
+  int64_t t_offset;
 };
+
+// the label map of one thread's VPT voxels: into `out`, or -- PEERS -- into every rank's gathered buffer
+template <typename OT, int VPT, bool PEERS>
+__device__ __forceinline__ void store_out(const VoteParams& p, int64_t t, int64_t v0, const bool (&on)[VPT]) {
+  if constexpr (PEERS) {
+    const int64_t off = (p.t_offset + t) * p.V + v0;
+    for (int r = 0; r < p.n_peers; ++r) store_labels<OT, VPT>(reinterpret_cast<OT*>(p.peers[r]) + off, on);
+  } else {
+    store_labels<OT, VPT>(reinterpret_cast<OT*>(p.out) + t * p.V + v0, on);
+  }
+}
 
 // softmax statistics of the N data parameters of target t: row max and 1/sum(exp(x - max)),
 // the two quantities torch.softmax's CPU kernel forms before scaling (consensus.ipynb:104).
@@ -205,7 +221,7 @@ __device__ __forceinline__ void softmax_stats(const float* __restrict__ dp, int6
   inv = 1.0f / s;
 }
 
-template <typename LT, typename OT, int LEVELS, bool TIES, bool VECP>
+template <typename LT, typename OT, int LEVELS, bool TIES, bool VECP, bool PEERS>
 __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
   using In = VoteIn<LT, VECP>;
   constexpr int VPT = In::VPT;
@@ -253,7 +269,6 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
 
   const int64_t u0 = p.units * chunk / p.chunks, u1 = p.units * (chunk + 1) / p.chunks;
   const LT* __restrict__ lab_t = reinterpret_cast<const LT*>(p.labels) + t * N * V;
-  OT* __restrict__ out_t = reinterpret_cast<OT*>(p.out) + t * V;
   unsigned int my_ties = 0u;
 
   for (int64_t base = u0; base < u1; base += kThreads) {
@@ -358,9 +373,10 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteParams p) {
           my_ties += (fabs(fg - bg) < 1e-6 * top) ? 1u : 0u;
         }
       }
-      store_labels<OT, VPT>(out_t + u * VPT, on);
+      store_out<OT, VPT, PEERS>(p, t, u * VPT, on);
     }
   }
+  if constexpr (PEERS) __threadfence_system();  // peer stores performed before the grid counts as complete
   // Programmatic dependent launch: this CTA has read all its labels and its map stores are fenced -- a vote (or loss)
   // kernel launched right behind this one may move in while the last CTAs finish (nothing it reads is written here; a
   // reused output buffer cannot see one of our stores arrive late).  The wait before exit keeps stream order for
@@ -446,7 +462,7 @@ __device__ __forceinline__ void warp_weights(const VoteParams& p, int64_t t, flo
   }
 }
 
-template <typename OT, int LEVELS, bool TIES>
+template <typename OT, int LEVELS, bool TIES, bool PEERS>
 __global__ void __launch_bounds__(kStgThreads, DS_VOTE_STG_MINB) vote_kernel_u8_staged(const VoteParams p) {
   using In = VoteIn<uint8_t, true>;
   constexpr int VPT = 16;
@@ -606,12 +622,13 @@ __global__ void __launch_bounds__(kStgThreads, DS_VOTE_STG_MINB) vote_kernel_u8_
               my_ties += (fabs(fg - bg) < 1e-6 * top) ? 1u : 0u;
             }
           }
-          store_labels<OT, VPT>(reinterpret_cast<OT*>(p.out) + t * V + u * VPT, on);
+          store_out<OT, VPT, PEERS>(p, t, u * VPT, on);
         }
       }
     }
   }
-  __threadfence();
+  if constexpr (PEERS) __threadfence_system();
+  else __threadfence();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (TIES) {
@@ -623,7 +640,7 @@ __global__ void __launch_bounds__(kStgThreads, DS_VOTE_STG_MINB) vote_kernel_u8_
 }
 
 // uint8 planes, many tiles per resident CTA, N <= 256, 16-byte aligned rows: the staged kernel
-template <typename OT>
+template <typename OT, bool PEERS>
 int launch_vote_staged(const VoteParams& p0, cudaStream_t stream) {
   VoteParams p = p0;
   p.units = p.V / 16;
@@ -631,8 +648,8 @@ int launch_vote_staged(const VoteParams& p0, cudaStream_t stream) {
   const bool ties = p.near_ties != nullptr;
   const int levels = p.N < 16 ? 1 : 2;  // N < 256: level 1 is never folded
   void (*kern)(const VoteParams) = nullptr;
-  if (levels == 1) kern = ties ? vote_kernel_u8_staged<OT, 1, true> : vote_kernel_u8_staged<OT, 1, false>;
-  else kern = ties ? vote_kernel_u8_staged<OT, 2, true> : vote_kernel_u8_staged<OT, 2, false>;
+  if (levels == 1) kern = ties ? vote_kernel_u8_staged<OT, 1, true, PEERS> : vote_kernel_u8_staged<OT, 1, false, PEERS>;
+  else kern = ties ? vote_kernel_u8_staged<OT, 2, true, PEERS> : vote_kernel_u8_staged<OT, 2, false, PEERS>;
   const size_t smem = (size_t)kStgStages * kStgStageBytes;
   static thread_local void (*occ_kern)(const VoteParams) = nullptr;
   static thread_local int occ_cached = 0;
@@ -660,7 +677,7 @@ int launch_vote_staged(const VoteParams& p0, cudaStream_t stream) {
   return check_launch("ds_consensus_vote");
 }
 
-template <typename LT, typename OT, bool VECP>
+template <typename LT, typename OT, bool VECP, bool PEERS>
 int launch_vote(const VoteParams& p0, cudaStream_t stream) {
   VoteParams p = p0;
   constexpr int VPT = VoteIn<LT, VECP>::VPT;
@@ -673,7 +690,7 @@ int launch_vote(const VoteParams& p0, cudaStream_t stream) {
   const bool ties = p.near_ties != nullptr;
   const int levels = p.N < 32 ? (p.N < 16 ? 1 : 2) : (p.N < 256 ? 2 : 4);
   void (*kern)(const VoteParams) = nullptr;
-#define DS_VOTE_PICK(L, TI) kern = vote_kernel<LT, OT, L, TI, VECP>
+#define DS_VOTE_PICK(L, TI) kern = vote_kernel<LT, OT, L, TI, VECP, PEERS>
   if (levels == 1) {
     if (ties) DS_VOTE_PICK(1, true); else DS_VOTE_PICK(1, false);
   } else if (levels == 2) {
@@ -745,12 +762,43 @@ int launch_vote(const VoteParams& p0, cudaStream_t stream) {
   return check_launch("ds_consensus_vote");
 }
 
-template <typename LT, typename OT>
+bool aligned16_everywhere(const VoteParams& p) {
+  if (reinterpret_cast<uintptr_t>(p.labels) % 16) return false;
+  if (p.n_peers == 0) return reinterpret_cast<uintptr_t>(p.out) % 16 == 0;
+  for (int r = 0; r < p.n_peers; ++r)
+    if (reinterpret_cast<uintptr_t>(p.peers[r]) % 16) return false;
+  return true;
+}
+
+template <typename LT, typename OT, bool PEERS>
 int dispatch_align(const VoteParams& p, cudaStream_t stream) {
   constexpr int VPT = VoteIn<LT, true>::VPT;
-  const bool vec = (p.V % VPT == 0) && (reinterpret_cast<uintptr_t>(p.labels) % 16 == 0) &&
-                   (reinterpret_cast<uintptr_t>(p.out) % 16 == 0);
-  return vec ? launch_vote<LT, OT, true>(p, stream) : launch_vote<LT, OT, false>(p, stream);
+  const bool vec = (p.V % VPT == 0) && aligned16_everywhere(p);
+  if constexpr (std::is_same<LT, uint8_t>::value) {
+    // uint8 planes with enough tiles to keep a persistent grid busy: the staged (bulk-copy) kernel
+    const int64_t tiles = p.T * ((p.V / 16 + kThreads - 1) / kThreads);
+    const bool staged = env_int("DS_VOTE_STAGED", 1) && vec && p.V % 16 == 0 && p.N < kStgMaxN &&
+                        tiles >= (int64_t)env_int("DS_VOTE_STG_MIN_TILES", 8) * 2 * sm_count();
+    if (staged) return launch_vote_staged<OT, PEERS>(p, stream);
+  }
+  return vec ? launch_vote<LT, OT, true, PEERS>(p, stream) : launch_vote<LT, OT, false, PEERS>(p, stream);
+}
+
+template <bool PEERS>
+int dispatch_dtypes(const VoteParams& p, int label_dtype, int out_dtype, cudaStream_t s) {
+  if (label_dtype == DS_I64)
+    return out_dtype == DS_I64 ? dispatch_align<int64_t, int64_t, PEERS>(p, s) : dispatch_align<int64_t, uint8_t, PEERS>(p, s);
+  return out_dtype == DS_I64 ? dispatch_align<uint8_t, int64_t, PEERS>(p, s) : dispatch_align<uint8_t, uint8_t, PEERS>(p, s);
+}
+
+int check_vote_args(const char* who, const void* labels, const float* weights, int label_dtype, int out_dtype, int64_t T,
+                    int64_t N, int64_t V) {
+  if (!labels || !weights) return fail(DS_ERR_NULL, "%s: labels and weights are required", who);
+  if (T <= 0 || N <= 0 || V <= 0) return fail(DS_ERR_SHAPE, "%s: T, N, V must be positive", who);
+  if (N > DS_MAX_CANDIDATES) return fail(DS_ERR_SHAPE, "%s: N=%lld exceeds %d", who, (long long)N, DS_MAX_CANDIDATES);
+  if ((label_dtype != DS_I64 && label_dtype != DS_U8) || (out_dtype != DS_I64 && out_dtype != DS_U8))
+    return fail(DS_ERR_DTYPE, "%s: labels/out must be DS_I64 or DS_U8", who);
+  return ds_device_check();
 }
 
 }  // namespace
@@ -760,23 +808,34 @@ extern "C" int ds_consensus_vote(const void* labels, int label_dtype, const floa
                                  int64_t T, int64_t N, int64_t V, void* out, int out_dtype,
                                  unsigned long long* near_tie_count, ds_stream_t stream) {
   using namespace ds;
-  if (!labels || !weights || !out) return fail(DS_ERR_NULL, "ds_consensus_vote: labels, weights and out are required");
-  if (T <= 0 || N <= 0 || V <= 0) return fail(DS_ERR_SHAPE, "ds_consensus_vote: T, N, V must be positive");
-  if (N > DS_MAX_CANDIDATES) return fail(DS_ERR_SHAPE, "ds_consensus_vote: N=%lld exceeds %d", (long long)N, DS_MAX_CANDIDATES);
-  if ((label_dtype != DS_I64 && label_dtype != DS_U8) || (out_dtype != DS_I64 && out_dtype != DS_U8))
-    return fail(DS_ERR_DTYPE, "ds_consensus_vote: labels/out must be DS_I64 or DS_U8");
-  if (int rc = ds_device_check()) return rc;
+  if (!out) return fail(DS_ERR_NULL, "ds_consensus_vote: labels, weights and out are required");
+  if (int rc = check_vote_args("ds_consensus_vote", labels, weights, label_dtype, out_dtype, T, N, V)) return rc;
   VoteParams p{};
   p.labels = labels, p.weights = weights, p.out = out, p.near_ties = near_tie_count;
   p.T = T, p.N = N, p.V = V, p.raw = weights_are_raw ? 1 : 0;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (label_dtype == DS_I64)
-    return out_dtype == DS_I64 ? dispatch_align<int64_t, int64_t>(p, s) : dispatch_align<int64_t, uint8_t>(p, s);
-  // uint8 planes with enough tiles to keep a persistent grid busy: the staged (bulk-copy) kernel
-  const int64_t tiles = T * ((V / 16 + kThreads - 1) / kThreads);
-  const bool staged = env_int("DS_VOTE_STAGED", 1) && V % 16 == 0 && N < kStgMaxN &&
-                      reinterpret_cast<uintptr_t>(labels) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
-                      tiles >= (int64_t)env_int("DS_VOTE_STG_MIN_TILES", 8) * 2 * sm_count();
-  if (staged) return out_dtype == DS_I64 ? launch_vote_staged<int64_t>(p, s) : launch_vote_staged<uint8_t>(p, s);
-  return out_dtype == DS_I64 ? dispatch_align<uint8_t, int64_t>(p, s) : dispatch_align<uint8_t, uint8_t>(p, s);
+  return dispatch_dtypes<false>(p, label_dtype, out_dtype, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ds_consensus_vote_gather(const void* labels, int label_dtype, const float* weights, int weights_are_raw,
+                                        int64_t T_local, int64_t N, int64_t V, int64_t t_offset, int64_t T_global,
+                                        void* const* gathered, int world_size, int out_dtype,
+                                        unsigned long long* near_tie_count, ds_stream_t stream) {
+  using namespace ds;
+  if (!gathered) return fail(DS_ERR_NULL, "ds_consensus_vote_gather: the table of gathered buffers is required");
+  if (world_size < 1 || world_size > DS_MAX_PEERS)
+    return fail(DS_ERR_ARG, "ds_consensus_vote_gather: world_size must be in [1, %d]", DS_MAX_PEERS);
+  if (t_offset < 0 || T_local < 0 || t_offset + T_local > T_global)
+    return fail(DS_ERR_ARG, "ds_consensus_vote_gather: rows [%lld, %lld) do not fit %lld targets", (long long)t_offset,
+                (long long)(t_offset + T_local), (long long)T_global);
+  if (T_local == 0) return 0;  // a rank without targets (more ranks than targets) stores nothing
+  if (int rc = check_vote_args("ds_consensus_vote_gather", labels, weights, label_dtype, out_dtype, T_local, N, V)) return rc;
+  VoteParams p{};
+  p.labels = labels, p.weights = weights, p.out = nullptr, p.near_ties = near_tie_count;
+  p.T = T_local, p.N = N, p.V = V, p.raw = weights_are_raw ? 1 : 0;
+  p.n_peers = world_size, p.t_offset = t_offset;
+  for (int r = 0; r < world_size; ++r) {
+    if (!gathered[r]) return fail(DS_ERR_NULL, "ds_consensus_vote_gather: gathered[%d] is NULL", r);
+    p.peers[r] = gathered[r];
+  }
+  return dispatch_dtypes<true>(p, label_dtype, out_dtype, reinterpret_cast<cudaStream_t>(stream));
 }

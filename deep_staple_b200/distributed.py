@@ -30,6 +30,7 @@ from . import _binding as _b
 
 __all__ = [
     "FusedExchange",
+    "VoteGather",
     "shard_range",
     "gather_batch_indices",
     "exchange_instance_stats",
@@ -109,6 +110,53 @@ class FusedExchange:
         return 0
 
 
+class VoteGather:
+    """Symmetric ``[T_global, V]`` label-map buffers for ``ds_consensus_vote_gather``: one buffer per rank, every
+    buffer mapped into every rank (``torch.distributed._symmetric_memory``: CUDA VMM / fabric handles), so the vote
+    kernel stores each consensus map straight into all ranks' copies over NVLink / NVSwitch while it is still reading
+    label planes -- the all-gather of the target-sharded consensus without a collective, a padding copy or a ``cat``.
+
+    Construction is COLLECTIVE (rendezvous).  ``barrier()`` orders the ranks on the current stream (signal pads of
+    the symmetric allocation; no NCCL kernel)."""
+
+    _cache = {}
+
+    def __init__(self, n_targets_global: int, voxels: int, dtype: torch.dtype, device: torch.device, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 16:
+            raise ValueError("VoteGather supports at most 16 ranks (DS_MAX_PEERS)")
+        self.buf = symm_mem.empty((n_targets_global, voxels), dtype=dtype, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        ptrs = [int(x) for x in self.handle.buffer_ptrs]
+        offset = self.buf.data_ptr() - ptrs[self.rank]  # the tensor may sit inside a larger symmetric block
+        self.table = (ctypes.c_void_p * self.world)(*[x + offset for x in ptrs])  # host table the C ABI takes
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    @classmethod
+    def get(cls, n_targets_global: int, voxels: int, dtype: torch.dtype, device: torch.device, group=None) -> "VoteGather":
+        """The buffers of (group, targets, voxels, dtype), built on first use (collective).  At most 4 are kept."""
+        key = (id(group), n_targets_global, voxels, dtype, device.index)
+        if key not in cls._cache:
+            if len(cls._cache) >= 4:
+                cls._cache.pop(next(iter(cls._cache)))
+            cls._cache[key] = cls(n_targets_global, voxels, dtype, device, group)
+        return cls._cache[key]
+
+    @classmethod
+    def clear_cache(cls) -> None:
+        cls._cache.clear()
+
+    def barrier(self) -> None:
+        self.handle.barrier(channel=0)
+
+
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous block of ``n_items`` owned by ``rank``: sizes differ by at most one, the first
     ``n_items % world_size`` ranks get the larger blocks (100 targets over 8 GPUs -> 13,13,13,13,12,...)."""
@@ -158,15 +206,32 @@ def sharded_consensus(
     count_near_ties: bool = False,
     group=None,
     vote_fn: Optional[Callable] = None,
+    fused: Optional[bool] = None,
+    out_dtype: Optional[torch.dtype] = None,
 ):
     """Vote on this rank's block of targets (``labels_local [T_r, N, *S]`` = targets
     ``shard_range(n_targets_global, rank, world)``); with ``gather`` every rank receives the full
-    ``[T_global, *S]`` stack (one all-gather, the only collective).  Returns ``(maps, near_ties)``."""
+    ``[T_global, *S]`` stack.  Returns ``(maps, near_ties)``.
+
+    ``fused`` (default: on for CUDA labels on more than one rank): the gather happens INSIDE the vote kernel --
+    ``ds_consensus_vote_gather`` stores every map into all ranks' ``VoteGather`` buffers over NVLink peer memory,
+    two stream-ordered barriers around it, no NCCL call; the returned stack is that buffer (valid until the next
+    fused call with the same shapes).  ``fused=False``: vote, then one NCCL all-gather.
+    ``out_dtype``: dtype of the gathered maps (default: the labels' dtype; ``torch.uint8`` skips the widening pass
+    -- the binary vote only ever emits 0 / 1 and the maps always TRAVEL as uint8)."""
     rank, world = _world(group)
     lo, hi = shard_range(n_targets_global, rank, world)
     if labels_local.shape[0] != hi - lo:
         raise ValueError(f"rank {rank} owns targets [{lo},{hi}) but got {labels_local.shape[0]} label stacks")
     ties = None
+    final_dtype = out_dtype or labels_local.dtype
+    if fused is None:
+        fused = gather and vote_fn is None and labels_local.is_cuda and world > 1
+    if fused:
+        if not gather or vote_fn is not None:
+            raise ValueError("fused=True is the gather inside the vote kernel: it needs gather=True and no vote_fn")
+        return _fused_vote_gather(labels_local, data_parameters_local, n_targets_global, lo, hi, count_near_ties, group,
+                                  final_dtype)
     # The binary vote only ever emits 0 / 1: with the gather ahead, int64 label stacks are voted into uint8 maps,
     # which travel 8x lighter through the all-gather (the collective, not the vote, is the expensive part: 1.7 GB
     # per rank for cfg3 as int64) and are widened back to the labels' dtype on arrival.
@@ -201,7 +266,35 @@ def sharded_consensus(
         a, b = shard_range(n_targets_global, r, world)
         parts.append(full[r * per : r * per + (b - a)])
     full = torch.cat(parts) if len(parts) > 1 and n_targets_global % world else full[:n_targets_global]
-    return (full.to(labels_local.dtype) if compact else full), ties
+    return (full.to(final_dtype) if full.dtype != final_dtype else full), ties
+
+
+def _fused_vote_gather(labels_local, dps_local, n_targets_global, lo, hi, count_near_ties, group, final_dtype):
+    """``sharded_consensus`` with the gather inside the vote kernel (see ``VoteGather``)."""
+    dev = labels_local.device
+    T_local, N = hi - lo, labels_local.shape[1]
+    spatial = tuple(labels_local.shape[2:])
+    V = 1
+    for s in spatial:
+        V *= s
+    wire = torch.uint8 if final_dtype in (torch.uint8, torch.int64) else final_dtype
+    vg = VoteGather.get(n_targets_global, V, wire, dev, group)
+    ties = torch.zeros((), dtype=torch.int64, device=dev) if count_near_ties else None
+    lab = labels_local.contiguous()
+    dps = dps_local.detach().to(device=dev, dtype=torch.float32).reshape(T_local, N).contiguous() if T_local else None
+    lib = _b.load()
+    with torch.cuda.device(dev):
+        vg.barrier()  # every rank is done reading the previous result out of its buffer
+        if T_local:
+            rc = lib.ds_consensus_vote_gather(
+                _b.ptr(lab), _b.label_dtype(lab), _b.ptr(dps), 1, T_local, N, V, lo, n_targets_global, vg.table, vg.world,
+                _b.label_dtype(vg.buf), _b.ptr(ties), _b.stream_ptr(dev))
+            _b.check(rc, "ds_consensus_vote_gather")
+        vg.barrier()  # every rank's rows have landed in every buffer
+    if count_near_ties:
+        dist.all_reduce(ties, op=dist.ReduceOp.SUM, group=group)
+    full = vg.buf.view(n_targets_global, *spatial)
+    return (full.to(final_dtype) if full.dtype != final_dtype else full), ties
 
 
 class _DistributedDPLoss(torch.autograd.Function):

@@ -104,6 +104,19 @@ int ds_consensus_vote(const void* labels, int label_dtype, const float* weights,
                       int64_t T, int64_t N, int64_t V, void* out, int out_dtype,
                       unsigned long long* near_tie_count, ds_stream_t stream);
 
+/* Fused vote + all-gather for the target-sharded consensus (the reference is single process):
+ * this rank votes its T_local targets (global rows t_offset .. t_offset + T_local - 1) and the kernel stores every
+ * label map straight into row t_offset + t of the [T_global, V] buffer of EVERY rank -- `gathered[r]` is rank r's
+ * buffer as mapped into this process (peer memory over NVLink / NVSwitch, e.g. torch symmetric memory or CUDA IPC;
+ * gathered[own rank] is the local buffer).  No collective and no staging copy: the transfer overlaps the vote.  The
+ * caller orders the ranks around the call (a barrier before: peers are done reading the previous result; a barrier
+ * after: every rank's rows have landed).  Other arguments as for ds_consensus_vote; world_size <= DS_MAX_PEERS. */
+#define DS_MAX_PEERS 16
+int ds_consensus_vote_gather(const void* labels, int label_dtype, const float* weights, int weights_are_raw,
+                             int64_t T_local, int64_t N, int64_t V, int64_t t_offset, int64_t T_global,
+                             void* const* gathered, int world_size, int out_dtype,
+                             unsigned long long* near_tie_count, ds_stream_t stream);
+
 /* EXTENSION (no reference counterpart): per-class weighted vote + argmax, ties -> lowest class.
  * 2 <= num_classes <= DS_MAX_CLASSES, N <= 255; labels outside [0,num_classes) cast no vote. */
 int ds_consensus_vote_multiclass(const void* labels, int label_dtype, const float* weights,

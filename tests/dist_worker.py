@@ -199,9 +199,34 @@ def main():
     labels = (torch.rand((T, N, *S), generator=gen) < 0.4).to(torch.uint8).to(dev)
     dps = torch.randn((T, N), generator=gen).to(dev)
     lo, hi = dd.shard_range(T, rank, world)
-    full, ties = dd.sharded_consensus(labels[lo:hi], dps[lo:hi], T, gather=True, count_near_ties=True)
     ref_c, ref_t = ds.consensus_batched(labels, dps, count_near_ties=True)
-    assert torch.equal(full, ref_c) and int(ties) == int(ref_t)
+    for fused in (False, True):  # NCCL all-gather after the vote / stores into every rank's buffer from inside the vote
+        full, ties = dd.sharded_consensus(labels[lo:hi], dps[lo:hi], T, gather=True, count_near_ties=True, fused=fused)
+        assert torch.equal(full, ref_c) and int(ties) == int(ref_t), f"sharded consensus, fused={fused}"
+    # the fused gather again: int64 label stacks (uint8 on the wire, widened on arrival), the staged uint8 kernel forced,
+    # ragged shards (T % world != 0 whenever world does not divide 5), repeated calls into the same symmetric buffers
+    lab64 = labels.long()
+    for rep in range(3):
+        full64, _ = dd.sharded_consensus(lab64[lo:hi], dps[lo:hi] + rep, T, fused=True)
+        ref64 = ds.consensus_batched(lab64, dps + rep)
+        assert full64.dtype == torch.int64 and torch.equal(full64, ref64), f"fused gather int64 rep {rep}"
+        full8, _ = dd.sharded_consensus(lab64[lo:hi], dps[lo:hi] + rep, T, fused=True, out_dtype=torch.uint8)
+        assert full8.dtype == torch.uint8 and torch.equal(full8.long(), ref64)
+    os.environ["DS_VOTE_STG_MIN_TILES"] = "0"
+    full, _ = dd.sharded_consensus(labels[lo:hi], dps[lo:hi], T, fused=True)
+    assert torch.equal(full, ref_c), "fused gather through the staged uint8 kernel"
+    del os.environ["DS_VOTE_STG_MIN_TILES"]
+    T2 = world + 1 if world > 1 else 3  # more ranks than full shares: some ranks own one target, rank 0 two
+    lab2 = (torch.rand((T2, 3, 8, 8, 16), generator=gen) < 0.5).to(torch.uint8).to(dev)
+    dps2 = torch.randn((T2, 3), generator=gen).to(dev)
+    lo2, hi2 = dd.shard_range(T2, rank, world)
+    full2, _ = dd.sharded_consensus(lab2[lo2:hi2], dps2[lo2:hi2], T2, fused=True)
+    assert torch.equal(full2, ds.consensus_batched(lab2, dps2))
+    lo3, hi3 = dd.shard_range(1, rank, world)  # one target: every rank but the first owns nothing
+    full3, _ = dd.sharded_consensus(lab2[:1][lo3:hi3], dps2[:1][lo3:hi3], 1, fused=True)
+    assert torch.equal(full3, ds.consensus_batched(lab2[:1], dps2[:1]))
+    if rank == 0:
+        print("FUSED_GATHER_OK", world)
     dist.barrier()
     if rank == 0:
         print("DIST_OK", world)
