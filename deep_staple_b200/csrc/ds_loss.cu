@@ -32,7 +32,7 @@ int setup_tiles(LossParams& p, const char* who, bool stats) {
   (void)who;
   p.steps_per_inst = (p.units + 31) / 32;
   p.n_steps = p.steps_per_inst * p.B_local;
-  int per_sm = env_int("DS_LOSS_CTAS_PER_SM", loss_min_blocks(p.units == p.V ? 0 : p.C, p.units * 8 == p.V ? 8 : 4));
+  int per_sm = env_int("DS_LOSS_CTAS_PER_SM", loss_min_blocks(p.units == p.V ? 0 : p.C, p.units * 8 == p.V ? 8 : 4, p.logit_bytes));
   if (p.use_tma) per_sm = env_int("DS_LOSS_TMA_CTAS_PER_SM", p.tma_min_blocks);
   int64_t grid = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
   const int64_t need = (p.n_steps + kWarps - 1) / kWarps;
@@ -91,7 +91,8 @@ int setup_tiles(LossParams& p, const char* who, bool stats) {
 
 int setup_geometry(LossParams& p, int logit_dtype, int target_dtype, bool* vec_out, const char* who, bool stats) {
   const int C = p.C;
-  const int W = (logit_dtype == DS_F32) ? 4 : (C <= 4 ? 8 : 4);
+  const int W = (logit_dtype == DS_F32) ? 4 : (C <= 4 ? (C == 3 ? DS_HALF_C3_VEC : 8) : 4);
+  p.logit_bytes = logit_dtype == DS_F32 ? 4 : 2;
   bool vec = (p.V % W == 0) && aligned16(p.logits) && aligned16(p.dlogits) && aligned16(p.target) &&
              aligned16(p.dice_target);
   if (env_int("DS_FORCE_SCALAR", 0)) vec = false;

@@ -80,6 +80,7 @@ struct LossParams {
   int C, use_risk, mode, finalize, dp_outputs, grid, groups;
   int use_tma;                           // launch the TMA-staged shell (ds_loss_tma.cuh)
   int tma_stages, tma_min_blocks;        // its ring depth and resident CTAs per SM for this variant (host side only)
+  int logit_bytes;                       // sizeof the logit type (host side only)
   const double* stats_smem;              // device-side only: statistics staged in shared memory for the epilogue
   // fused multi-GPU exchange (ds_dp_loss_fwd_bwd_exchange): peer-mapped exchange buffers, see finish_launch
   const unsigned long long* peer_bases;  // device array [world]: base address of every rank's exchange buffer
@@ -889,11 +890,18 @@ struct StepWalk {
 // Resident CTAs per SM the register allocation is held to: the binary kernels fit 64 registers
 // without spilling; more classes keep more logits / gradients live and get a looser bound (a
 // spilling build of the run-time-C kernel was both slow and numerically off).
-constexpr int loss_min_blocks(int C, int VEC) {
-  return C == 2 ? (VEC <= 4 ? DS_LOSS_MIN_BLOCKS : 3) : (C == 3 ? 3 : (C == 4 ? 2 : 1));
+#ifndef DS_HALF_C3_VEC
+#define DS_HALF_C3_VEC 8   // voxels per thread and step of the half-precision three-class kernels (8 or 4)
+#endif
+#ifndef DS_HALF_C3_MINB
+#define DS_HALF_C3_MINB 3  // their resident CTAs per SM
+#endif
+constexpr int loss_min_blocks(int C, int VEC, int logit_bytes = 4) {
+  return C == 2 ? (VEC <= 4 ? DS_LOSS_MIN_BLOCKS : 3)
+                : (C == 3 ? (logit_bytes == 2 ? DS_HALF_C3_MINB : 3) : (C == 4 ? 2 : 1));
 }
 template <typename LT, typename TT, int C, int VEC, bool GRAD, bool STATS, bool DICE>
-__global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC)) loss_kernel(const LossParams p) {
+__global__ void __launch_bounds__(kThreads, loss_min_blocks(C, VEC, (int)sizeof(LT))) loss_kernel(const LossParams p) {
   constexpr int CC = C == 0 ? DS_MAX_CLASSES : C;
   const int nc = C == 0 ? p.C : C;
   __shared__ double s_scratch[kWarps + 1];

@@ -61,7 +61,7 @@ int launch_tt(const LossParams& p, bool grad, bool stats, bool vec, cudaStream_t
   constexpr int W = sizeof(LT) == 4 ? 4 : 8;
   switch (p.C) {
     case 2: return launch_cfg<LT, TT, 2, W>(p, grad, stats, stream);
-    case 3: return launch_cfg<LT, TT, 3, W>(p, grad, stats, stream);
+    case 3: return launch_cfg<LT, TT, 3, (sizeof(LT) == 2 ? DS_HALF_C3_VEC : W)>(p, grad, stats, stream);
     case 4: return launch_cfg<LT, TT, 4, W>(p, grad, stats, stream);
     default: return launch_cfg<LT, TT, 0, 4>(p, grad, stats, stream);
   }

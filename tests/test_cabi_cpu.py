@@ -70,6 +70,21 @@ def test_argument_validation_happens_before_any_device_work(lib):
     assert lib.ds_dp_loss_fwd_bwd(fake, 7, fake, 3, None, 2, 2, 64, fake, None, 2, 0, None, 1, None, None, fake, fake,
                                   fake, fake, fake, 1 << 20, None) == -2  # unknown logits dtype
     assert lib.ds_rescale_inplace(fake, 0, 0, fake, fake, None) == -3
+    # fused vote + gather: the peer table, the world size and the row range are checked before anything else
+    table = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    assert lib.ds_consensus_vote_gather(fake, 4, fake, 1, 1, 2, 64, 0, 2, None, 2, 4, None, None) == -1
+    assert lib.ds_consensus_vote_gather(fake, 4, fake, 1, 1, 2, 64, 0, 2, table, 0, 4, None, None) == -6   # world_size 0
+    assert lib.ds_consensus_vote_gather(fake, 4, fake, 1, 1, 2, 64, 0, 2, table, 17, 4, None, None) == -6  # > DS_MAX_PEERS
+    assert lib.ds_consensus_vote_gather(fake, 4, fake, 1, 2, 2, 64, 1, 2, table, 2, 4, None, None) == -6   # rows 1..2 of 2
+    assert lib.ds_consensus_vote_gather(fake, 4, fake, 1, 0, 2, 64, 2, 2, table, 2, 4, None, None) == 0    # an empty shard
+    assert lib.ds_consensus_vote_gather(fake, 0, fake, 1, 1, 2, 64, 0, 2, table, 2, 4, None, None) == -2   # f32 labels
+    hole = (ctypes.c_void_p * 2)(0x1000, None)
+    if torch.cuda.is_available():
+        assert lib.ds_consensus_vote_gather(fake, 4, fake, 1, 1, 2, 64, 0, 2, hole, 2, 4, None, None) == -1
+    # host label packer
+    assert lib.ds_host_narrow_labels(None, fake, 8, 1) == -1
+    assert lib.ds_host_narrow_labels(fake, fake, -1, 1) == -3
+    assert lib.ds_host_narrow_labels(fake, fake, 0, 1) == 0
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
@@ -81,6 +96,8 @@ def test_no_cpu_fallback_without_a_gpu(lib):
     # valid arguments, but no B200: the entry points refuse instead of computing something on the host
     assert lib.ds_consensus_vote(fake, 3, fake, 1, 1, 2, 8, fake, 3, None, None) == -5
     assert lib.ds_label_stats(fake, 3, None, 3, 1, 2, 8, fake, fake, 1 << 20, None) == -5
+    table = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    assert lib.ds_consensus_vote_gather(fake, 4, fake, 1, 1, 2, 64, 0, 2, table, 2, 4, None, None) == -5
     assert lib.ds_launch_count() == 0
     lbl = torch.zeros((4, 4, 4), dtype=torch.long)
     with pytest.raises(RuntimeError, match="no CPU fallback"):

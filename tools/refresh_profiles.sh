@@ -11,6 +11,8 @@ python bench.py --workload vote > gpurun_out/${R}_bench_vote_n1.json 2>> gpurun_
 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${R}_bench_reference_arm.json 2>> gpurun_out/${R}_bench_n1.err
 python tools/configs_bench.py > gpurun_out/${R}_configs.log 2>&1; cat gpurun_out/${R}_configs.log
 python tools/host_overhead.py > gpurun_out/${R}_host_overhead.log 2>&1; cat gpurun_out/${R}_host_overhead.log
+python tools/host_pack_bench.py > gpurun_out/${R}_host_pack_bench.log 2>&1
+python tools/tune_vote_staged.py > gpurun_out/${R}_vote_u8_staged_tune.log 2>&1
 python tools/launch_gap.py > gpurun_out/${R}_launch_gap.log 2>&1; python tools/launch_gap.py 64 2 1 256 256 >> gpurun_out/${R}_launch_gap.log 2>&1
 # launch list of the bench command (cold-cache, serialised: compare shares, not absolutes)
 python bench.py --steps 4 --warmup 3 --skip-cpu --e2e-steps 2 --skip-configs > gpurun_out/plain.log 2>&1 &&
