@@ -903,6 +903,11 @@ def vote_section(device, rank, world, steps, warmup, peak, dist, dtypes=("int64"
         out[name] = rec
         del labels, res
         torch.cuda.empty_cache()
+        # Returning tens of GB to the driver leaves the GPU busy for a while after cudaFree returns (the first ~25 ms of
+        # launches after freeing the 50 GB int64 stack ran 20 % slow -- 1.17 vs 0.97 ms for the uint8 vote, same buffers,
+        # same kernel; tools/vote_u8_history2.py): let it settle before the next dtype is timed.
+        torch.cuda.synchronize()
+        time.sleep(0.5)
     return out
 
 

@@ -10,6 +10,7 @@
 // and reproduces the summation ORDER of ATen's CPU sum(dim=0) (rows sequential inside blocks of
 // 16, each full block folded into the next accumulator level), so that for identical weights the
 // fp32 vote -- and therefore the thresholded label -- is bit-identical to the reference.
+#include <cstdio>
 #include <type_traits>
 
 #include "ds_common.cuh"
@@ -110,8 +111,9 @@ struct VoteIn<uint8_t, true> {
 #pragma unroll
     for (int i = 0; i < W; ++i) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (r.w[i] & (1u << (8 * j))) acc[4 * i + j] = __fadd_rn(acc[4 * i + j], w);
+      for (int j = 0; j < 4; ++j)  // whole-byte masks: a single LOP3 with a predicate result for every byte (the 0x1 mask of
+                                   // byte 0 compiled to LOP3 + ISETP); equivalent here, every byte of a binary batch is 0 or 1
+        if (r.w[i] & (0xffu << (8 * j))) acc[4 * i + j] = __fadd_rn(acc[4 * i + j], w);
     }
   }
 };
@@ -656,6 +658,10 @@ int launch_vote_staged(const VoteParams& p0, cudaStream_t stream) {
   if (occ_kern != kern) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return fail(DS_ERR_ARG, "ds_consensus_vote: %zu bytes of shared memory refused", smem);
+    // two CTAs per SM need ~210 KB of the SM's 228 KB as shared memory: ask for the maximum carve-out explicitly instead of
+    // leaving it to the driver's per-launch heuristic (which had the kernel at 1.17 ms instead of 0.97 ms inside bench.py's
+    // default run, after the loss kernels, with identical grid and occupancy report)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int o = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kStgThreads, smem) != cudaSuccess || o < 1) o = 1;
     occ_kern = kern, occ_cached = o;
@@ -672,6 +678,9 @@ int launch_vote_staged(const VoteParams& p0, cudaStream_t stream) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+  if (env_int("DS_VOTE_DEBUG", 0))
+    fprintf(stderr, "[ds_vote] staged kernel: grid %lld x %d threads, %zu B ring, occupancy %d, run %d, T %lld N %lld V %lld\n",
+            (long long)grid, kStgThreads, smem, occ_cached, p.run, (long long)p.T, (long long)p.N, (long long)p.V);
   cudaLaunchKernelEx(&cfg, kern, p);
   count_launch();
   return check_launch("ds_consensus_vote");
@@ -748,6 +757,9 @@ int launch_vote(const VoteParams& p0, cudaStream_t stream) {
   if (p.T * want > 0x7fffffffLL) return fail(DS_ERR_SHAPE, "ds_consensus_vote: T*chunks exceeds the grid limit");
   p.chunks = (int)want;
   const dim3 grid((unsigned)(p.T * want));
+  if (env_int("DS_VOTE_DEBUG", 0))
+    fprintf(stderr, "[ds_vote] LDG kernel: grid %lld (%d chunks per target), label bytes %d, vector path %d, T %lld N %lld V %lld\n",
+            (long long)(p.T * want), p.chunks, (int)sizeof(LT), (int)VECP, (long long)p.T, (long long)p.N, (long long)p.V);
   {
     static const bool pdl = env_int("DS_VOTE_PDL", 1) != 0;
     cudaLaunchConfig_t cfg = {};
