@@ -19,6 +19,7 @@
 
 #include <immintrin.h>
 #include <stdint.h>
+#include <pthread.h>
 
 #include "deep_staple_b200.h"
 
@@ -31,7 +32,17 @@ namespace {
 class HostPool {
  public:
   static HostPool& get() {
-    static HostPool* pool = new HostPool();  // never destroyed: worker threads outlive static destruction order
+    // never destroyed: worker threads outlive static destruction order.  A forked child (a DataLoader worker that
+    // packs labels itself) inherits the object but none of its threads: the atfork handler makes the child start a
+    // pool of its own; the inherited one is left alone (its mutexes may have been held at the time of the fork).
+    static std::once_flag once;
+    std::call_once(once, [] { pthread_atfork(nullptr, nullptr, [] { instance().store(nullptr); }); });
+    HostPool* pool = instance().load(std::memory_order_acquire);
+    if (!pool) {
+      HostPool* fresh = new HostPool();
+      if (instance().compare_exchange_strong(pool, fresh)) pool = fresh;
+      else delete fresh;  // another caller was first; `fresh` has no threads yet
+    }
     return *pool;
   }
   // runs fn(i) for i in [0, n) on up to `threads` threads (the caller takes part), returns when all are done
@@ -52,6 +63,10 @@ class HostPool {
   }
 
  private:
+  static std::atomic<HostPool*>& instance() {
+    static std::atomic<HostPool*> p{nullptr};
+    return p;
+  }
   void work() {
     for (int i; (i = next_.fetch_add(1)) < n_;) (*fn_)(i);
   }

@@ -85,3 +85,26 @@ def test_concurrent_callers_share_the_pool():
     [t.join() for t in ts]
     for x, o in zip(xs, outs):
         assert torch.equal(o, x.to(torch.uint8))
+
+
+def test_forked_child_gets_its_own_pool():
+    """A forked process (a DataLoader worker) inherits the pool object but none of its threads: it must start a pool
+    of its own instead of waiting for helpers that do not exist.  Runs in a fresh interpreter: the parent uses the
+    pool, forks, the child packs with helper threads and reports through its exit code."""
+    code = (
+        "import os, sys, torch, deep_staple_b200 as ds\n"
+        "torch.set_num_threads(1)\n"  # torch's own OpenMP team does not survive a fork either: keep it out of the test
+        "x = torch.arange(3_000_000, dtype=torch.int64) % 251\n"
+        "ref = x.to(torch.uint8)\n"
+        "assert torch.equal(ds.narrow_labels_host(x, threads=4), ref)\n"
+        "pid = os.fork()\n"
+        "if pid == 0:\n"
+        "    ok = all(torch.equal(ds.narrow_labels_host(x, threads=4), ref) for _ in range(3))\n"
+        "    os._exit(0 if ok else 7)\n"
+        "_, status = os.waitpid(pid, 0)\n"
+        "assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0, status\n"
+        "assert torch.equal(ds.narrow_labels_host(x, threads=4), ref)\n"
+    )
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True,
+                         text=True, timeout=120)
+    assert res.returncode == 0, res.stderr[-2000:]

@@ -11,9 +11,6 @@ python bench.py --workload vote > gpurun_out/${R}_bench_vote_n1.json 2>> gpurun_
 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${R}_bench_reference_arm.json 2>> gpurun_out/${R}_bench_n1.err
 python tools/configs_bench.py > gpurun_out/${R}_configs.log 2>&1; cat gpurun_out/${R}_configs.log
 python tools/host_overhead.py > gpurun_out/${R}_host_overhead.log 2>&1; cat gpurun_out/${R}_host_overhead.log
-python tools/host_pack_bench.py > gpurun_out/${R}_host_pack_bench.log 2>&1
-python tools/tune_vote_staged.py > gpurun_out/${R}_vote_u8_staged_tune.log 2>&1
-python tools/launch_gap.py > gpurun_out/${R}_launch_gap.log 2>&1; python tools/launch_gap.py 64 2 1 256 256 >> gpurun_out/${R}_launch_gap.log 2>&1
 # launch list of the bench command (cold-cache, serialised: compare shares, not absolutes)
 python bench.py --steps 4 --warmup 3 --skip-cpu --e2e-steps 2 --skip-configs > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${R}_launches.csv \
@@ -38,4 +35,8 @@ cap loss_f32_c3 loss_kernel 3 python tools/prof_case.py f32 i64 8 3 192 160 160
 cap vote_u8 vote_kernel 2 python tools/prof_vote.py u8 13 30
 cap vote_i64 vote_kernel 2 python tools/prof_vote.py i64 13 30
 rm -f gpurun_out/plain*.log
+# lower-priority logs last: a call cut short by its time limit keeps everything above
+python tools/host_pack_bench.py > gpurun_out/${R}_host_pack_bench.log 2>&1
+python tools/tune_vote_staged.py > gpurun_out/${R}_vote_u8_staged_tune.log 2>&1
+python tools/launch_gap.py > gpurun_out/${R}_launch_gap.log 2>&1; python tools/launch_gap.py 64 2 1 256 256 >> gpurun_out/${R}_launch_gap.log 2>&1
 ls -la gpurun_out | tail -40
