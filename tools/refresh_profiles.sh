@@ -15,6 +15,7 @@ python tools/host_overhead.py > gpurun_out/${R}_host_overhead.log 2>&1; cat gpur
 python bench.py --steps 4 --warmup 3 --skip-cpu --e2e-steps 2 --skip-configs > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${R}_launches.csv \
     python bench.py --steps 4 --warmup 3 --skip-cpu --e2e-steps 2 --skip-configs > gpurun_out/ncu_list.log 2>&1
+python tools/launches_summary.py gpurun_out/${R}_launches.csv > gpurun_out/${R}_launches_table.txt 2>&1
 # the dominant kernels, one full capture each; the reports are read ON the box (a report with imported sources is
 # ~50 MB, gpurun_out/ carries 64 MB back): raw metrics + summary + per-line source view as text, then the report goes
 cap() {  # cap <name> <kernel regex> <skip> <command...>
