@@ -60,7 +60,8 @@ class LabelUploader:
 
     A staging slot is reused only after the copy that last read it has completed (event per slot), so the
     packer of step k + 1 runs while the copy of step k is in flight.  The returned uint8 device tensor is
-    owned by the uploader and valid until the call after next (``slots`` calls later)."""
+    owned by the uploader and valid until the call after next (``slots`` calls later).  uint8 host labels (packed
+    earlier, e.g. in a data-loader worker) are copied as they are."""
 
     def __init__(self, shape, device, slots: int = 2, threads: Optional[int] = None):
         self.device = torch.device(device)
@@ -80,9 +81,20 @@ class LabelUploader:
         self._i += 1
         if self._copied[k] is not None:
             self._copied[k].synchronize()  # the previous copy out of this slot
-        narrow_labels_host(labels, self._staging[k], self.threads)
         dst = self._device[k] if out is None else out
-        dst.copy_(self._staging[k], non_blocking=True)
+        if labels.dtype is torch.uint8 and not labels.is_cuda:
+            # packed already (e.g. by ``narrow_labels_host`` in a data-loader worker): nothing to do on this thread
+            # but the copy -- straight out of the caller's tensor when it is pinned, through the staging slot otherwise
+            if tuple(labels.shape) != self.shape:
+                raise ValueError(f"labels have shape {tuple(labels.shape)}, the uploader was built for {self.shape}")
+            src = labels if labels.is_contiguous() else labels.contiguous()
+            if not src.is_pinned():
+                self._staging[k].copy_(src)
+                src = self._staging[k]
+            dst.copy_(src, non_blocking=True)
+        else:
+            narrow_labels_host(labels, self._staging[k], self.threads)
+            dst.copy_(self._staging[k], non_blocking=True)
         ev = self._copied[k] or torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._copied[k] = ev

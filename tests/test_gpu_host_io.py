@@ -66,3 +66,24 @@ def test_calc_dp_consensus_from_host_volumes_takes_the_packed_path(cuda_device):
     big[0] *= 300
     out_big = ds.calc_dp_consensus(list(big), dps)
     assert torch.equal(out_big, ds.calc_dp_consensus(list(big.to(cuda_device)), dps).cpu())
+
+
+def test_label_uploader_takes_labels_packed_earlier(cuda_device):
+    """uint8 host labels (packed by ``narrow_labels_host`` in a data-loader worker) are copied as they are: pinned,
+    pageable and non-contiguous sources, over more steps than there are staging slots; wrong shapes are refused."""
+    import deep_staple_b200 as ds
+
+    gen = torch.Generator().manual_seed(4)
+    shape = (3, 10, 12, 16)
+    up = ds.LabelUploader(shape, cuda_device)
+    for step in range(5):
+        target = torch.randint(0, 4, shape, generator=gen)
+        packed = ds.narrow_labels_host(target)
+        ref = target.to(torch.uint8)
+        for src in (packed, packed.pin_memory(), packed.transpose(1, 2).contiguous().transpose(1, 2)):
+            got = up(src)
+            assert got.dtype == torch.uint8 and got.device.type == "cuda"
+            assert torch.equal(got.cpu(), ref), f"step {step}"
+        assert torch.equal(up(target).cpu(), ref)  # the int64 route through the same slots
+    with pytest.raises(ValueError):
+        up(torch.zeros((3, 10, 12, 15), dtype=torch.uint8))
